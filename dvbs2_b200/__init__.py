@@ -1,0 +1,11 @@
+"""dvbs2_b200 — B200-native DVB-S2 baseband decode chain (demapper, LDPC NMS, BCH) behind libdvbs2_cuda.
+
+Only the hot path lives here: csrc/ (CUDA kernels + the C ABI) and the host-side mirror of the reference's module
+interface.  Nothing in this package imports oracle/.
+"""
+from . import capi  # noqa: F401
+from .modules import (Decoder_BCH_DVBS2_cuda, Decoder_chain_DVBS2_cuda, Decoder_LDPC_DVBS2_cuda, Handle,  # noqa: F401
+                      Interleaver_DVBS2_cuda, Modem_DVBS2_cuda)
+
+__all__ = ["capi", "Handle", "Modem_DVBS2_cuda", "Interleaver_DVBS2_cuda", "Decoder_LDPC_DVBS2_cuda",
+           "Decoder_BCH_DVBS2_cuda", "Decoder_chain_DVBS2_cuda"]

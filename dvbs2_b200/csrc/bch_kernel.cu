@@ -1,0 +1,285 @@
+// BCH (N_bch, K_bch, t = 12) hard decoder over GF(2^14), shortened from 16383, sm_100a.
+//
+// Semantics (bit-exact): src/common/Module/Decoder_BCH_DVBS2/Decoder_BCH_DVBS2.cpp:28-40 (DVB-S2 bit order: the first
+// transmitted bit is the highest-degree coefficient) around lib/aff3ct/src/Module/Decoder/BCH/Standard/
+// Decoder_BCH_std.cpp:52-221: syndromes S_1..S_24, Berlekamp's iterative algorithm aborted once the locator degree
+// exceeds t, Chien search over ALL 16383 field elements, success iff #roots == locator degree, flips only inside the
+// shortened length, payload = first K bits, CWD = success.
+//
+// B200 mapping:
+//   * Syndromes are where the reference spends its time (24 x N table look-ups per frame).  Here the received word
+//     stays bit-sliced across the 32 frames of a group (one u32 per code bit, exactly the hd words the LDPC kernel
+//     leaves in HBM), and each thread divides it by ONE of the 12 degree-14 minimal polynomials with a bit-sliced
+//     LFSR: 14 state words, ~7 XORs per code bit for 32 frames at once.  S_j is then a fixed GF(2)-linear map of the
+//     remainder modulo the minimal polynomial of alpha^j (conjugates share it), so all 24 syndromes cost 12 divisions.
+//   * Only frames with a non-zero remainder (rare after a converged LDPC word) go on: one warp per such frame runs
+//     Berlekamp-Massey on lane 0 (the minimal LFSR is unique whenever its length <= t, so any BM yields the
+//     reference's polynomial; longer ones are failures in both) and a 32-lane Chien search; corrections are applied
+//     to the bit-sliced words with atomicXor.
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace dvbs2
+{
+namespace
+{
+// minimal polynomials of alpha^(2p+1), p = 0..11, for p(x) = 1 + x + x^3 + x^5 + x^14 (bit k = coefficient of x^k);
+// dvbs2_cuda_create() checks them against the ones it derives from the field (code_tables.cpp).
+__host__ __device__ constexpr unsigned
+minpoly_const(int p)
+{
+    constexpr unsigned t[BCH_NPOLY] = { 0x402b, 0x4941, 0x4647, 0x5591, 0x6b55, 0x6389,
+                                        0x6ce5, 0x4f21, 0x460f, 0x5a49, 0x5811, 0x65ef };
+    return t[p];
+}
+
+template<int P>
+__device__ __forceinline__ void
+lfsr_step(uint32_t (&s)[GF_M], uint32_t in)
+{
+    constexpr unsigned MP = minpoly_const(P);
+    const uint32_t fb = s[GF_M - 1];
+#pragma unroll
+    for (int k = GF_M - 1; k >= 1; k--)
+        s[k] = ((MP >> k) & 1u) ? (s[k - 1] ^ fb) : s[k - 1];
+    s[0] = in ^ fb; // every minimal polynomial has constant term 1
+}
+
+template<int P>
+__device__ void
+remainder_one(const BchLaunch& a, int g)
+{
+    uint32_t s[GF_M];
+#pragma unroll
+    for (int k = 0; k < GF_M; k++)
+        s[k] = 0;
+    const uint4* w = reinterpret_cast<const uint4*>(a.words + (size_t)g * a.stride);
+    const int n4 = a.N / 4;
+#pragma unroll 2
+    for (int i = 0; i < n4; i++)
+    {
+        const uint4 q = __ldg(w + i);
+        lfsr_step<P>(s, q.x);
+        lfsr_step<P>(s, q.y);
+        lfsr_step<P>(s, q.z);
+        lfsr_step<P>(s, q.w);
+    }
+    for (int i = n4 * 4; i < a.N; i++)
+        lfsr_step<P>(s, a.words[(size_t)g * a.stride + i]);
+    uint32_t any = 0;
+    uint32_t* r = a.rem + ((size_t)g * BCH_NPOLY + P) * GF_M;
+#pragma unroll
+    for (int k = 0; k < GF_M; k++)
+    {
+        r[k] = s[k];
+        any |= s[k];
+    }
+    if (any) atomicOr(a.nz + g, any);
+}
+
+// grid: (ceil(groups / 128), 12 polynomials); thread = (group, polynomial)
+__global__ void __launch_bounds__(128) bch_remainder_kernel(const BchLaunch a)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.n_groups) return;
+    switch (blockIdx.y)
+    {
+        case 0: remainder_one<0>(a, g); break;
+        case 1: remainder_one<1>(a, g); break;
+        case 2: remainder_one<2>(a, g); break;
+        case 3: remainder_one<3>(a, g); break;
+        case 4: remainder_one<4>(a, g); break;
+        case 5: remainder_one<5>(a, g); break;
+        case 6: remainder_one<6>(a, g); break;
+        case 7: remainder_one<7>(a, g); break;
+        case 8: remainder_one<8>(a, g); break;
+        case 9: remainder_one<9>(a, g); break;
+        case 10: remainder_one<10>(a, g); break;
+        case 11: remainder_one<11>(a, g); break;
+    }
+}
+
+struct GF
+{
+    const uint16_t* __restrict__ exp;
+    const int16_t* __restrict__ log;
+    __device__ unsigned mul(unsigned x, unsigned y) const
+    {
+        if (!x || !y) return 0;
+        int e = __ldg(log + x) + __ldg(log + y);
+        if (e >= GF_N) e -= GF_N;
+        return __ldg(exp + e);
+    }
+    __device__ unsigned div(unsigned x, unsigned y) const // y != 0
+    {
+        if (!x) return 0;
+        int e = __ldg(log + x) - __ldg(log + y);
+        if (e < 0) e += GF_N;
+        return __ldg(exp + e);
+    }
+};
+
+constexpr int BCH_FRAMES_PER_BLOCK = 4;
+// one warp per frame; frames with a zero syndrome leave immediately
+__global__ void __launch_bounds__(BCH_FRAMES_PER_BLOCK * 32) bch_correct_kernel(const BchLaunch a, const BchDevTables t)
+{
+    __shared__ unsigned sh_S[BCH_FRAMES_PER_BLOCK][2 * BCH_T + 2];
+    __shared__ int sh_lam_log[BCH_FRAMES_PER_BLOCK][BCH_T + 2]; // log of locator coefficients, -1 = zero
+    __shared__ int sh_L[BCH_FRAMES_PER_BLOCK];
+    __shared__ int sh_loc[BCH_FRAMES_PER_BLOCK][BCH_T + 4];
+    __shared__ int sh_cnt[BCH_FRAMES_PER_BLOCK];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int frame = blockIdx.x * BCH_FRAMES_PER_BLOCK + warp;
+    if (frame >= a.n_frames) return;
+    const int g = frame >> 5, f = frame & 31;
+    if (!((a.nz[g] >> f) & 1u))
+    {
+        if (lane == 0 && a.cwd) a.cwd[frame] = 1;
+        return;
+    }
+    const GF gf{ t.alpha_to, t.index_of };
+
+    // syndromes in polynomial form: S_j = sum_k rem_{poly_of[j]}[k] alpha^(jk)
+    if (lane >= 1 && lane <= 2 * BCH_T)
+    {
+        const uint32_t* r = a.rem + ((size_t)g * BCH_NPOLY + t.poly_of[lane]) * GF_M;
+        unsigned acc = 0;
+#pragma unroll
+        for (int k = 0; k < GF_M; k++)
+            if ((r[k] >> f) & 1u) acc ^= t.synd_mat[lane][k];
+        sh_S[warp][lane] = acc;
+    }
+    if (lane == 0) sh_cnt[warp] = 0;
+    __syncwarp();
+
+    if (lane == 0)
+    {
+        // Berlekamp-Massey; C = current connection polynomial, B = last one before a length change
+        unsigned Cp[BCH_T + 2], Bp[BCH_T + 2], Tp[BCH_T + 2];
+#pragma unroll
+        for (int i = 0; i < BCH_T + 2; i++)
+            Cp[i] = Bp[i] = 0;
+        Cp[0] = Bp[0] = 1;
+        int L = 0, m = 1;
+        unsigned b = 1;
+        bool fail = false;
+        const unsigned* S = sh_S[warp];
+        for (int n = 0; n < 2 * BCH_T && !fail; n++)
+        {
+            unsigned d = S[n + 1];
+            for (int i = 1; i <= L; i++)
+                d ^= gf.mul(Cp[i], S[n + 1 - i]);
+            if (d == 0)
+            {
+                m++;
+                continue;
+            }
+            const unsigned coef = gf.div(d, b);
+            if (2 * L <= n)
+            {
+                const int newL = n + 1 - L;
+                if (newL > BCH_T)
+                {
+                    fail = true;
+                    L = newL;
+                    break;
+                }
+                for (int i = 0; i < BCH_T + 2; i++)
+                    Tp[i] = Cp[i];
+                for (int i = 0; i + m < BCH_T + 2; i++)
+                    Cp[i + m] ^= gf.mul(coef, Bp[i]);
+                for (int i = 0; i < BCH_T + 2; i++)
+                    Bp[i] = Tp[i];
+                L = newL, b = d, m = 1;
+            }
+            else
+            {
+                for (int i = 0; i + m < BCH_T + 2; i++)
+                    Cp[i + m] ^= gf.mul(coef, Bp[i]);
+                m++;
+            }
+        }
+        sh_L[warp] = fail ? -1 : L;
+        for (int j = 0; j <= BCH_T; j++)
+            sh_lam_log[warp][j] = Cp[j] ? (int)__ldg(t.index_of + Cp[j]) : -1;
+    }
+    __syncwarp();
+
+    const int L = sh_L[warp];
+    bool ok = false;
+    if (L >= 0)
+    {
+        // Chien search: Lambda(alpha^i) for i = 1..16383, lanes interleaved; root at i <-> error location 16383 - i
+        int e[BCH_T + 1];
+#pragma unroll
+        for (int j = 1; j <= BCH_T; j++)
+        {
+            const int lg = sh_lam_log[warp][j];
+            e[j] = (j <= L && lg >= 0) ? (lg + j * (lane + 1)) % GF_N : -1;
+        }
+        for (int i = lane + 1; i <= GF_N; i += 32)
+        {
+            unsigned q = 1;
+#pragma unroll
+            for (int j = 1; j <= BCH_T; j++)
+                if (e[j] >= 0)
+                {
+                    q ^= __ldg(t.alpha_to + e[j]);
+                    e[j] += 32 * j;
+                    if (e[j] >= GF_N) e[j] -= GF_N; // 32*12 < 16383: one subtraction suffices
+                }
+            if (q == 0)
+            {
+                const int slot = atomicAdd(&sh_cnt[warp], 1);
+                if (slot < BCH_T + 4) sh_loc[warp][slot] = GF_N - i;
+            }
+        }
+        __syncwarp();
+        const int cnt = sh_cnt[warp];
+        if (cnt == L)
+        {
+            ok = true;
+            if (lane < cnt)
+            {
+                const int loc = sh_loc[warp][lane];
+                if (loc < a.N) atomicXor(a.words + (size_t)g * a.stride + (a.N - 1 - loc), 1u << f);
+            }
+        }
+    }
+    if (lane == 0)
+    {
+        if (a.cwd) a.cwd[frame] = (int8_t)ok;
+        if (a.stats)
+        {
+            atomicAdd(a.stats + STAT_BCH_NONZERO, 1ull);
+            if (!ok) atomicAdd(a.stats + STAT_BCH_FAIL, 1ull);
+        }
+    }
+}
+} // namespace
+
+bool
+bch_minpoly_matches(const BchTables& t)
+{
+    for (int p = 0; p < BCH_NPOLY; p++)
+        if ((minpoly_const(p) & 0x3FFFu) != t.minpoly[p] || !(minpoly_const(p) >> GF_M)) return false;
+    return true;
+}
+
+cudaError_t
+launch_bch_decode(const BchLaunch& a, const BchDevTables& t, cudaStream_t s)
+{
+    cudaError_t e = cudaMemsetAsync(a.nz, 0, sizeof(uint32_t) * a.n_groups, s);
+    if (e != cudaSuccess) return e;
+    const dim3 grid((a.n_groups + 127) / 128, BCH_NPOLY);
+    bch_remainder_kernel<<<grid, 128, 0, s>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int blocks = (a.n_frames + BCH_FRAMES_PER_BLOCK - 1) / BCH_FRAMES_PER_BLOCK;
+    bch_correct_kernel<<<blocks, BCH_FRAMES_PER_BLOCK * 32, 0, s>>>(a, t);
+    return cudaGetLastError();
+}
+} // namespace dvbs2

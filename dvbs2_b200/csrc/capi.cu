@@ -1,0 +1,603 @@
+// C ABI of libdvbs2_cuda (include/dvbs2_cuda.h): handle, device buffers, stream plumbing.  No compute here.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/dvbs2_cuda.h"
+#include "kernels.h"
+
+namespace dvbs2
+{
+bool bch_minpoly_matches(const BchTables& t); // bch_kernel.cu
+}
+using namespace dvbs2;
+
+namespace
+{
+constexpr int N_PIPE = 3; // streams used to overlap H2D / compute / D2H in the host-buffer entry points
+
+struct DevBuf
+{
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+} // namespace
+
+struct dvbs2_cuda_handle
+{
+    dvbs2_cuda_cfg cfg{};
+    ModcodParams mc{};
+    LdpcTables lt;
+    int max_frames = 0, max_groups = 0;
+    int k8 = 0;
+    size_t elt = 4; // sizeof(R)
+    cudaStream_t stream = nullptr;
+    cudaStream_t pipe[N_PIPE] = {};
+    cudaEvent_t pipe_done[N_PIPE] = {};
+    // code tables
+    uint16_t* d_idx = nullptr;
+    uint16_t* d_alpha_to = nullptr;
+    int16_t* d_index_of = nullptr;
+    float* d_cstl = nullptr;
+    BchDevTables bch{};
+    // decoder state
+    DevBuf var, cn, hd, out_hd, rem, nz, cwd_ldpc, cwd_bch, nit, stats;
+    // staging for the host-buffer entry points (grown on demand, never beyond max_frames)
+    DevBuf in_a, in_b, out_a, sigma;
+    uint64_t launches = 0;
+    std::string last_error;
+};
+
+namespace
+{
+int
+fail_cuda(dvbs2_cuda_handle* h, cudaError_t e, const char* what)
+{
+    if (h)
+    {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+        h->last_error = buf;
+    }
+    cudaGetLastError(); // clear sticky-less errors
+    return e == cudaErrorMemoryAllocation ? DVBS2_ERR_NOMEM : DVBS2_ERR_CUDA;
+}
+
+#define CU(h, call)                                                                                                    \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e__ = (call);                                                                                      \
+        if (e__ != cudaSuccess) return fail_cuda((h), e__, #call);                                                     \
+    } while (0)
+
+int
+ensure(dvbs2_cuda_handle* h, DevBuf& b, size_t bytes)
+{
+    if (b.bytes >= bytes) return DVBS2_OK;
+    if (b.p) CU(h, cudaFree(b.p));
+    b.p = nullptr, b.bytes = 0;
+    CU(h, cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+    return DVBS2_OK;
+}
+
+#define TRY(expr)                                                                                                      \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        int rc__ = (expr);                                                                                             \
+        if (rc__ != DVBS2_OK) return rc__;                                                                             \
+    } while (0)
+
+int
+check_frames(dvbs2_cuda_handle* h, int n_frames)
+{
+    if (!h || n_frames < 0) return DVBS2_ERR_INVALID;
+    if (n_frames > h->max_frames) return DVBS2_ERR_TOO_MANY;
+    return DVBS2_OK;
+}
+
+LdpcLaunch
+ldpc_args(dvbs2_cuda_handle* h, int first_group, int n_frames, int8_t* cwd, int32_t* n_iter)
+{
+    LdpcLaunch a{};
+    a.var = (char*)h->var.p + (size_t)first_group * N_LDPC * 32 * h->elt;
+    a.cn = (uint4*)h->cn.p + (size_t)first_group * h->mc.M * 32;
+    a.hd = (uint32_t*)h->hd.p + (size_t)first_group * N_LDPC;
+    a.out_hd = (uint32_t*)h->out_hd.p + (size_t)first_group * N_LDPC;
+    a.idx = h->d_idx;
+    a.cwd = cwd;
+    a.n_iter = n_iter;
+    a.stats = (unsigned long long*)h->stats.p;
+    a.n_frames = n_frames;
+    a.n_groups = (n_frames + 31) / 32;
+    a.K = h->mc.N_bch, a.M = h->mc.M, a.d_info = h->mc.d_info;
+    a.n_ite = h->cfg.n_ite, a.norm = h->cfg.norm, a.k8 = h->k8, a.early_stop = h->cfg.early_stop;
+    return a;
+}
+
+BchLaunch
+bch_args(dvbs2_cuda_handle* h, int first_group, int n_frames, int8_t* cwd)
+{
+    BchLaunch b{};
+    b.words = (uint32_t*)h->out_hd.p + (size_t)first_group * N_LDPC;
+    b.stride = N_LDPC;
+    b.rem = (uint32_t*)h->rem.p + (size_t)first_group * BCH_NPOLY * GF_M;
+    b.nz = (uint32_t*)h->nz.p + first_group;
+    b.cwd = cwd;
+    b.stats = (unsigned long long*)h->stats.p;
+    b.n_frames = n_frames, b.n_groups = (n_frames + 31) / 32;
+    b.N = h->mc.N_bch, b.K = h->mc.K_bch;
+    return b;
+}
+
+DemapLaunch
+demap_args(dvbs2_cuda_handle* h, const float* d_sigma, const float* d_sym, int n_frames)
+{
+    DemapLaunch d{};
+    d.sigma = d_sigma, d.sym = d_sym, d.cstl = h->d_cstl, d.n_frames = n_frames;
+    d.bps = h->mc.bps, d.n_sym = h->mc.n_sym, d.itl_cols = h->mc.itl_cols, d.itl_rev = h->mc.itl_rev;
+    d.quant_dec = h->cfg.quant_dec, d.quant_bits = h->cfg.quant_bits;
+    return d;
+}
+
+// device-side pieces, all asynchronous on `s`; frames occupy groups [first_group, ...)
+int
+run_ldpc(dvbs2_cuda_handle* h, cudaStream_t s, int first_group, const void* d_Y, int8_t* d_cwd, int32_t* d_VK,
+         int32_t* d_nit, int n_frames)
+{
+    if (n_frames == 0) return DVBS2_OK;
+    void* var = (char*)h->var.p + (size_t)first_group * N_LDPC * 32 * h->elt;
+    CU(h, launch_pack_llr(d_Y, var, h->cfg.precision, n_frames, s));
+    CU(h, launch_ldpc_decode(ldpc_args(h, first_group, n_frames, d_cwd, d_nit), h->cfg.precision, s));
+    CU(h, launch_unpack_bits((uint32_t*)h->out_hd.p + (size_t)first_group * N_LDPC, d_VK, N_LDPC, h->mc.N_bch, n_frames, s));
+    h->launches += 3;
+    return DVBS2_OK;
+}
+
+int
+run_bch(dvbs2_cuda_handle* h, cudaStream_t s, int first_group, const int32_t* d_Y, int8_t* d_cwd, int32_t* d_VK,
+        int n_frames)
+{
+    if (n_frames == 0) return DVBS2_OK;
+    uint32_t* words = (uint32_t*)h->out_hd.p + (size_t)first_group * N_LDPC;
+    CU(h, launch_pack_bits(d_Y, words, N_LDPC, h->mc.N_bch, n_frames, s));
+    CU(h, launch_bch_decode(bch_args(h, first_group, n_frames, d_cwd), h->bch, s));
+    CU(h, launch_unpack_bits(words, d_VK, N_LDPC, h->mc.K_bch, n_frames, s));
+    h->launches += 4;
+    return DVBS2_OK;
+}
+
+int
+run_chain(dvbs2_cuda_handle* h, cudaStream_t s, int first_group, const float* d_sigma, const float* d_sym,
+          int8_t* d_cwd_ldpc, int8_t* d_cwd_bch, int32_t* d_VK, int32_t* d_nit, int n_frames)
+{
+    if (n_frames == 0) return DVBS2_OK;
+    void* var = (char*)h->var.p + (size_t)first_group * N_LDPC * 32 * h->elt;
+    CU(h, launch_demap_to_var(demap_args(h, d_sigma, d_sym, n_frames), var, h->cfg.precision, s));
+    CU(h, launch_ldpc_decode(ldpc_args(h, first_group, n_frames, d_cwd_ldpc, d_nit), h->cfg.precision, s));
+    CU(h, launch_bch_decode(bch_args(h, first_group, n_frames, d_cwd_bch), h->bch, s));
+    CU(h, launch_unpack_bits((uint32_t*)h->out_hd.p + (size_t)first_group * N_LDPC, d_VK, N_LDPC, h->mc.K_bch, n_frames, s));
+    h->launches += 5;
+    return DVBS2_OK;
+}
+
+// chunking of a host batch over the pipeline streams: chunks are whole groups so their device regions are disjoint
+int
+chunk_frames(const dvbs2_cuda_handle* h, int n_frames)
+{
+    int per = (n_frames + N_PIPE * 2 - 1) / (N_PIPE * 2); // ~6 chunks per call
+    per = std::max(per, 4096);                             // below this the kernels are launch/latency bound anyway
+    per = (per + 31) / 32 * 32;
+    (void)h;
+    return per;
+}
+} // namespace
+
+extern "C"
+{
+    void dvbs2_cuda_default_cfg(dvbs2_cuda_cfg* cfg)
+    {
+        if (!cfg) return;
+        memset(cfg, 0, sizeof(*cfg));
+        cfg->modcod = DVBS2_QPSK_S_8_9;
+        cfg->n_ite = 10;
+        cfg->norm = 1.0f;
+        cfg->precision = DVBS2_PREC_F32;
+        cfg->early_stop = 1;
+        cfg->max_frames = 1024;
+        cfg->device = 0;
+        cfg->quant_bits = 6;
+        cfg->quant_dec = 2;
+    }
+
+    int dvbs2_cuda_device_count(void)
+    {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return 0;
+        }
+        return n;
+    }
+
+    const char* dvbs2_cuda_strerror(int status)
+    {
+        switch (status)
+        {
+            case DVBS2_OK: return "success";
+            case DVBS2_ERR_INVALID: return "invalid argument or unsupported configuration";
+            case DVBS2_ERR_CUDA: return "CUDA runtime error";
+            case DVBS2_ERR_TOO_MANY: return "n_frames exceeds the handle's max_frames";
+            case DVBS2_ERR_NOMEM: return "out of memory";
+        }
+        return "unknown status";
+    }
+
+    const char* dvbs2_cuda_last_error(const dvbs2_cuda_handle* h) { return h ? h->last_error.c_str() : ""; }
+
+    int dvbs2_cuda_destroy(dvbs2_cuda_handle* h)
+    {
+        if (!h) return DVBS2_OK;
+        cudaSetDevice(h->cfg.device);
+        for (DevBuf* b : { &h->var, &h->cn, &h->hd, &h->out_hd, &h->rem, &h->nz, &h->cwd_ldpc, &h->cwd_bch, &h->nit,
+                           &h->stats, &h->in_a, &h->in_b, &h->out_a, &h->sigma })
+            if (b->p) cudaFree(b->p);
+        for (void* p : { (void*)h->d_idx, (void*)h->d_alpha_to, (void*)h->d_index_of, (void*)h->d_cstl })
+            if (p) cudaFree(p);
+        for (int i = 0; i < N_PIPE; i++)
+        {
+            if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
+            if (h->pipe_done[i]) cudaEventDestroy(h->pipe_done[i]);
+        }
+        if (h->stream) cudaStreamDestroy(h->stream);
+        delete h;
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_create(const dvbs2_cuda_cfg* cfg, dvbs2_cuda_handle** out)
+    {
+        if (!cfg || !out) return DVBS2_ERR_INVALID;
+        *out = nullptr;
+        ModcodParams mc;
+        if (!modcod_params(cfg->modcod, mc)) return DVBS2_ERR_INVALID;
+        if (cfg->n_ite < 1 || cfg->max_frames < 1 || cfg->precision < 0 || cfg->precision > 2) return DVBS2_ERR_INVALID;
+        if (!(cfg->norm > 0.f) || cfg->norm > 1.f) return DVBS2_ERR_INVALID;
+        int k8 = 0;
+        for (int k = 1; k <= 8; k++)
+            if (cfg->norm == 0.125f * (float)k) k8 = k;
+        // integer decoders only know k/8 factors (Update_rule_NMS.hxx:14-39 throws otherwise)
+        if (cfg->precision != DVBS2_PREC_F32 && k8 == 0) return DVBS2_ERR_INVALID;
+        if (cfg->precision != DVBS2_PREC_F32)
+        {
+            const int type_bits = cfg->precision == DVBS2_PREC_I16 ? 16 : 8;
+            if (cfg->quant_dec <= 0 || cfg->quant_bits < 2 || cfg->quant_dec > cfg->quant_bits || cfg->quant_bits > type_bits)
+                return DVBS2_ERR_INVALID; // Quantizer_pow2.cpp:81-122
+        }
+        int ndev = dvbs2_cuda_device_count();
+        if (ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) return DVBS2_ERR_CUDA; // no CPU fallback
+
+        dvbs2_cuda_handle* h = new (std::nothrow) dvbs2_cuda_handle();
+        if (!h) return DVBS2_ERR_NOMEM;
+        h->cfg = *cfg;
+        h->mc = mc;
+        h->k8 = k8;
+        h->elt = cfg->precision == DVBS2_PREC_F32 ? 4 : cfg->precision == DVBS2_PREC_I16 ? 2 : 1;
+        h->max_groups = (cfg->max_frames + 31) / 32;
+        h->max_frames = h->max_groups * 32;
+
+        auto bail = [&](int rc) {
+            dvbs2_cuda_destroy(h);
+            return rc;
+        };
+#define CUB(call)                                                                                                      \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e__ = (call);                                                                                      \
+        if (e__ != cudaSuccess) return bail(fail_cuda(h, e__, #call));                                                 \
+    } while (0)
+
+        CUB(cudaSetDevice(cfg->device));
+        BchTables bt;
+        std::vector<float> cstl;
+        try
+        {
+            h->lt = build_ldpc_tables(mc.N_bch);
+            bt = build_bch_tables();
+            cstl = build_constellation(mc.bps);
+        }
+        catch (const std::exception& e)
+        {
+            h->last_error = e.what();
+            return bail(DVBS2_ERR_INVALID);
+        }
+        if (h->lt.d_info != mc.d_info || h->lt.M != mc.M || !bch_minpoly_matches(bt)) return bail(DVBS2_ERR_INVALID);
+
+        CUB(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        for (int i = 0; i < N_PIPE; i++)
+        {
+            CUB(cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking));
+            CUB(cudaEventCreateWithFlags(&h->pipe_done[i], cudaEventDisableTiming));
+        }
+        CUB(cudaMalloc(&h->d_idx, h->lt.idx.size() * sizeof(uint16_t)));
+        CUB(cudaMemcpy(h->d_idx, h->lt.idx.data(), h->lt.idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&h->d_alpha_to, bt.alpha_to.size() * sizeof(uint16_t)));
+        CUB(cudaMemcpy(h->d_alpha_to, bt.alpha_to.data(), bt.alpha_to.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&h->d_index_of, bt.index_of.size() * sizeof(int16_t)));
+        CUB(cudaMemcpy(h->d_index_of, bt.index_of.data(), bt.index_of.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&h->d_cstl, cstl.size() * sizeof(float)));
+        CUB(cudaMemcpy(h->d_cstl, cstl.data(), cstl.size() * sizeof(float), cudaMemcpyHostToDevice));
+        h->bch.alpha_to = h->d_alpha_to, h->bch.index_of = h->d_index_of;
+        memcpy(h->bch.minpoly, bt.minpoly, sizeof(bt.minpoly));
+        memcpy(h->bch.poly_of, bt.poly_of, sizeof(bt.poly_of));
+        memcpy(h->bch.synd_mat, bt.synd_mat, sizeof(bt.synd_mat));
+
+        const size_t G = (size_t)h->max_groups, F = (size_t)h->max_frames;
+        int rc;
+        if ((rc = ensure(h, h->var, G * N_LDPC * 32 * h->elt)) || (rc = ensure(h, h->cn, G * mc.M * 32 * sizeof(uint4))) ||
+            (rc = ensure(h, h->hd, G * N_LDPC * 4)) || (rc = ensure(h, h->out_hd, G * N_LDPC * 4)) ||
+            (rc = ensure(h, h->rem, G * BCH_NPOLY * GF_M * 4)) || (rc = ensure(h, h->nz, G * 4)) ||
+            (rc = ensure(h, h->cwd_ldpc, F)) || (rc = ensure(h, h->cwd_bch, F)) || (rc = ensure(h, h->nit, F * 4)) ||
+            (rc = ensure(h, h->stats, STAT_COUNT * sizeof(unsigned long long))))
+            return bail(rc);
+        CUB(cudaMemset(h->stats.p, 0, h->stats.bytes));
+        CUB(cudaMemset(h->out_hd.p, 0, h->out_hd.bytes));
+        CUB(cudaDeviceSynchronize());
+#undef CUB
+        *out = h;
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_get_info(const dvbs2_cuda_handle* h, dvbs2_cuda_info* info)
+    {
+        if (!h || !info) return DVBS2_ERR_INVALID;
+        info->K_bch = h->mc.K_bch, info->N_bch = h->mc.N_bch, info->K_ldpc = h->mc.N_bch, info->N_ldpc = N_LDPC;
+        info->bps = h->mc.bps, info->n_sym = h->mc.n_sym, info->M_ldpc = h->mc.M, info->E_ldpc = h->lt.E;
+        info->max_frames = h->max_frames;
+        return DVBS2_OK;
+    }
+
+    void* dvbs2_cuda_stream(dvbs2_cuda_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+    int dvbs2_cuda_sync(dvbs2_cuda_handle* h)
+    {
+        if (!h) return DVBS2_ERR_INVALID;
+        CU(h, cudaSetDevice(h->cfg.device));
+        CU(h, cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < N_PIPE; i++)
+            CU(h, cudaStreamSynchronize(h->pipe[i]));
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_get_stats(dvbs2_cuda_handle* h, dvbs2_cuda_stats* st)
+    {
+        if (!h || !st) return DVBS2_ERR_INVALID;
+        TRY(dvbs2_cuda_sync(h));
+        unsigned long long v[STAT_COUNT];
+        CU(h, cudaMemcpy(v, h->stats.p, sizeof(v), cudaMemcpyDeviceToHost));
+        st->frames = v[STAT_FRAMES], st->ldpc_iterations = v[STAT_LDPC_ITERS], st->ldpc_failures = v[STAT_LDPC_FAIL];
+        st->bch_nonzero = v[STAT_BCH_NONZERO], st->bch_failures = v[STAT_BCH_FAIL];
+        st->kernel_launches = h->launches;
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_reset_stats(dvbs2_cuda_handle* h)
+    {
+        if (!h) return DVBS2_ERR_INVALID;
+        TRY(dvbs2_cuda_sync(h));
+        CU(h, cudaMemset(h->stats.p, 0, h->stats.bytes));
+        h->launches = 0;
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_host_register(dvbs2_cuda_handle* h, void* ptr, size_t bytes)
+    {
+        if (!h || !ptr) return DVBS2_ERR_INVALID;
+        CU(h, cudaSetDevice(h->cfg.device));
+        CU(h, cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+        return DVBS2_OK;
+    }
+    int dvbs2_cuda_host_unregister(dvbs2_cuda_handle* h, void* ptr)
+    {
+        if (!h || !ptr) return DVBS2_ERR_INVALID;
+        CU(h, cudaHostUnregister(ptr));
+        return DVBS2_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------ device-pointer API
+    int dvbs2_cuda_demodulate_dev(dvbs2_cuda_handle* h, const float* d_CP, const float* d_Y_N1, float* d_Y_N2,
+                                  int deinterleave, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!d_CP || !d_Y_N1 || !d_Y_N2) return DVBS2_ERR_INVALID;
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        CU(h, launch_demap_frames(demap_args(h, d_CP, d_Y_N1, n_frames), d_Y_N2, deinterleave, h->stream));
+        h->launches += 1;
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_ldpc_decode_siho_dev(dvbs2_cuda_handle* h, const void* d_Y_N, int8_t* d_CWD, int32_t* d_V_K,
+                                        int32_t* d_n_iter, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!d_Y_N || !d_V_K) return DVBS2_ERR_INVALID;
+        CU(h, cudaSetDevice(h->cfg.device));
+        return run_ldpc(h, h->stream, 0, d_Y_N, d_CWD, d_V_K, d_n_iter, n_frames);
+    }
+
+    int dvbs2_cuda_bch_decode_hiho_dev(dvbs2_cuda_handle* h, const int32_t* d_Y_N, int8_t* d_CWD, int32_t* d_V_K,
+                                       int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!d_Y_N || !d_V_K) return DVBS2_ERR_INVALID;
+        CU(h, cudaSetDevice(h->cfg.device));
+        return run_bch(h, h->stream, 0, d_Y_N, d_CWD, d_V_K, n_frames);
+    }
+
+    int dvbs2_cuda_chain_dev(dvbs2_cuda_handle* h, const float* d_CP, const float* d_Y_N1, int8_t* d_CWD_ldpc,
+                             int8_t* d_CWD_bch, int32_t* d_V_K, int32_t* d_n_iter, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!d_CP || !d_Y_N1 || !d_V_K) return DVBS2_ERR_INVALID;
+        CU(h, cudaSetDevice(h->cfg.device));
+        return run_chain(h, h->stream, 0, d_CP, d_Y_N1, d_CWD_ldpc, d_CWD_bch, d_V_K, d_n_iter, n_frames);
+    }
+
+    // ------------------------------------------------------------------------------------------ host-pointer API
+    int dvbs2_cuda_demodulate(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, float* Y_N2, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!CP || !Y_N1 || !Y_N2) return DVBS2_ERR_INVALID;
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        const size_t symf = (size_t)2 * h->mc.n_sym * sizeof(float), llrf = (size_t)N_LDPC * sizeof(float);
+        TRY(ensure(h, h->in_a, symf * n_frames));
+        TRY(ensure(h, h->out_a, llrf * n_frames));
+        TRY(ensure(h, h->sigma, sizeof(float) * n_frames));
+        cudaStream_t s = h->stream;
+        CU(h, cudaMemcpyAsync(h->sigma.p, CP, sizeof(float) * n_frames, cudaMemcpyHostToDevice, s));
+        CU(h, cudaMemcpyAsync(h->in_a.p, Y_N1, symf * n_frames, cudaMemcpyHostToDevice, s));
+        CU(h, launch_demap_frames(demap_args(h, (float*)h->sigma.p, (float*)h->in_a.p, n_frames), (float*)h->out_a.p, 0, s));
+        h->launches += 1;
+        CU(h, cudaMemcpyAsync(Y_N2, h->out_a.p, llrf * n_frames, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaStreamSynchronize(s));
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_deinterleave(dvbs2_cuda_handle* h, const float* itl, float* nat, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!itl || !nat) return DVBS2_ERR_INVALID;
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        const size_t llrf = (size_t)N_LDPC * sizeof(float);
+        TRY(ensure(h, h->in_a, llrf * n_frames));
+        TRY(ensure(h, h->out_a, llrf * n_frames));
+        cudaStream_t s = h->stream;
+        CU(h, cudaMemcpyAsync(h->in_a.p, itl, llrf * n_frames, cudaMemcpyHostToDevice, s));
+        CU(h, launch_deinterleave((float*)h->in_a.p, (float*)h->out_a.p, n_frames, h->mc.n_sym, h->mc.itl_cols,
+                                  h->mc.itl_rev, s));
+        h->launches += 1;
+        CU(h, cudaMemcpyAsync(nat, h->out_a.p, llrf * n_frames, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaStreamSynchronize(s));
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_quantize(dvbs2_cuda_handle* h, const float* in, void* out, size_t n)
+    {
+        if (!h || !in || !out || h->cfg.precision == DVBS2_PREC_F32) return DVBS2_ERR_INVALID;
+        if (n == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        TRY(ensure(h, h->in_a, n * sizeof(float)));
+        TRY(ensure(h, h->out_a, n * h->elt));
+        cudaStream_t s = h->stream;
+        CU(h, cudaMemcpyAsync(h->in_a.p, in, n * sizeof(float), cudaMemcpyHostToDevice, s));
+        CU(h, launch_quantize((float*)h->in_a.p, h->out_a.p, h->cfg.precision, n, h->cfg.quant_dec, h->cfg.quant_bits, s));
+        h->launches += 1;
+        CU(h, cudaMemcpyAsync(out, h->out_a.p, n * h->elt, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaStreamSynchronize(s));
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_ldpc_decode_siho(dvbs2_cuda_handle* h, const void* Y_N, int8_t* CWD, int32_t* V_K, int32_t* n_iter,
+                                    int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!Y_N || !V_K) return DVBS2_ERR_INVALID;
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        const size_t inf = (size_t)N_LDPC * h->elt, outf = (size_t)h->mc.N_bch * sizeof(int32_t);
+        TRY(ensure(h, h->in_a, inf * n_frames));
+        TRY(ensure(h, h->out_a, outf * n_frames));
+        const int per = chunk_frames(h, n_frames);
+        int ci = 0;
+        for (int f0 = 0; f0 < n_frames; f0 += per, ci++)
+        {
+            const int nf = std::min(per, n_frames - f0);
+            cudaStream_t s = h->pipe[ci % N_PIPE];
+            char* d_in = (char*)h->in_a.p + inf * f0;
+            int32_t* d_out = (int32_t*)((char*)h->out_a.p + outf * f0);
+            int8_t* d_cwd = (int8_t*)h->cwd_ldpc.p + f0;
+            int32_t* d_nit = (int32_t*)h->nit.p + f0;
+            CU(h, cudaMemcpyAsync(d_in, (const char*)Y_N + inf * f0, inf * nf, cudaMemcpyHostToDevice, s));
+            TRY(run_ldpc(h, s, f0 / 32, d_in, d_cwd, d_out, d_nit, nf));
+            CU(h, cudaMemcpyAsync((char*)V_K + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
+            if (CWD) CU(h, cudaMemcpyAsync(CWD + f0, d_cwd, nf, cudaMemcpyDeviceToHost, s));
+            if (n_iter) CU(h, cudaMemcpyAsync(n_iter + f0, d_nit, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, s));
+        }
+        for (int i = 0; i < N_PIPE; i++)
+            CU(h, cudaStreamSynchronize(h->pipe[i]));
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_bch_decode_hiho(dvbs2_cuda_handle* h, const int32_t* Y_N, int8_t* CWD, int32_t* V_K, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!Y_N || !V_K) return DVBS2_ERR_INVALID;
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        const size_t inf = (size_t)h->mc.N_bch * sizeof(int32_t), outf = (size_t)h->mc.K_bch * sizeof(int32_t);
+        TRY(ensure(h, h->in_a, inf * n_frames));
+        TRY(ensure(h, h->out_a, outf * n_frames));
+        const int per = chunk_frames(h, n_frames);
+        int ci = 0;
+        for (int f0 = 0; f0 < n_frames; f0 += per, ci++)
+        {
+            const int nf = std::min(per, n_frames - f0);
+            cudaStream_t s = h->pipe[ci % N_PIPE];
+            int32_t* d_in = (int32_t*)((char*)h->in_a.p + inf * f0);
+            int32_t* d_out = (int32_t*)((char*)h->out_a.p + outf * f0);
+            int8_t* d_cwd = (int8_t*)h->cwd_bch.p + f0;
+            CU(h, cudaMemcpyAsync(d_in, (const char*)Y_N + inf * f0, inf * nf, cudaMemcpyHostToDevice, s));
+            TRY(run_bch(h, s, f0 / 32, d_in, d_cwd, d_out, nf));
+            CU(h, cudaMemcpyAsync((char*)V_K + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
+            if (CWD) CU(h, cudaMemcpyAsync(CWD + f0, d_cwd, nf, cudaMemcpyDeviceToHost, s));
+        }
+        for (int i = 0; i < N_PIPE; i++)
+            CU(h, cudaStreamSynchronize(h->pipe[i]));
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_chain(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
+                         int32_t* V_K, int32_t* n_iter, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!CP || !Y_N1 || !V_K) return DVBS2_ERR_INVALID;
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        const size_t inf = (size_t)2 * h->mc.n_sym * sizeof(float), outf = (size_t)h->mc.K_bch * sizeof(int32_t);
+        TRY(ensure(h, h->in_a, inf * n_frames));
+        TRY(ensure(h, h->out_a, outf * n_frames));
+        TRY(ensure(h, h->sigma, sizeof(float) * n_frames));
+        const int per = chunk_frames(h, n_frames);
+        int ci = 0;
+        for (int f0 = 0; f0 < n_frames; f0 += per, ci++)
+        {
+            const int nf = std::min(per, n_frames - f0);
+            cudaStream_t s = h->pipe[ci % N_PIPE];
+            float* d_sym = (float*)((char*)h->in_a.p + inf * f0);
+            float* d_sig = (float*)h->sigma.p + f0;
+            int32_t* d_out = (int32_t*)((char*)h->out_a.p + outf * f0);
+            int8_t* d_c1 = (int8_t*)h->cwd_ldpc.p + f0;
+            int8_t* d_c2 = (int8_t*)h->cwd_bch.p + f0;
+            int32_t* d_nit = (int32_t*)h->nit.p + f0;
+            CU(h, cudaMemcpyAsync(d_sig, CP + f0, sizeof(float) * nf, cudaMemcpyHostToDevice, s));
+            CU(h, cudaMemcpyAsync(d_sym, (const char*)Y_N1 + inf * f0, inf * nf, cudaMemcpyHostToDevice, s));
+            TRY(run_chain(h, s, f0 / 32, d_sig, d_sym, d_c1, d_c2, d_out, d_nit, nf));
+            CU(h, cudaMemcpyAsync((char*)V_K + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
+            if (CWD_ldpc) CU(h, cudaMemcpyAsync(CWD_ldpc + f0, d_c1, nf, cudaMemcpyDeviceToHost, s));
+            if (CWD_bch) CU(h, cudaMemcpyAsync(CWD_bch + f0, d_c2, nf, cudaMemcpyDeviceToHost, s));
+            if (n_iter) CU(h, cudaMemcpyAsync(n_iter + f0, d_nit, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, s));
+        }
+        for (int i = 0; i < N_PIPE; i++)
+            CU(h, cudaStreamSynchronize(h->pipe[i]));
+        return DVBS2_OK;
+    }
+}

@@ -1,0 +1,88 @@
+// Internal launch interfaces between capi.cu and the kernel translation units.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "code_tables.h"
+
+namespace dvbs2
+{
+constexpr int LDPC_WARPS_PER_BLOCK = 4;
+
+enum StatSlot
+{
+    STAT_FRAMES = 0,
+    STAT_LDPC_ITERS,
+    STAT_LDPC_FAIL,
+    STAT_BCH_NONZERO,
+    STAT_BCH_FAIL,
+    STAT_COUNT
+};
+
+// Device-resident layout shared by the kernels ("group" = 32 consecutive frames, lane = frame % 32):
+//   var    [groups][16200][32]  R       variable-node values (LLR + messages), lane-interleaved
+//   cn     [groups][M][32]      uint4   compressed check state {out1, out2, sign bits, eq bits}
+//   hd     [groups][16200]      u32     running hard decisions, bit f = frame f of the group
+//   out_hd [groups][16200]      u32     hard decisions snapshotted when each frame stopped iterating
+struct LdpcLaunch
+{
+    void* var;
+    uint4* cn;
+    uint32_t* hd;
+    uint32_t* out_hd;
+    const uint16_t* idx; // [M][d_pad]
+    int8_t* cwd;         // [frames] or null
+    int32_t* n_iter;     // [frames] or null
+    unsigned long long* stats;
+    int n_frames, n_groups;
+    int K, M, d_info;
+    int n_ite;
+    float norm;
+    int k8; // norm * 8 if that is an integer in 1..8, else 0
+    int early_stop;
+};
+
+cudaError_t launch_ldpc_decode(const LdpcLaunch& a, int precision, cudaStream_t s);
+cudaError_t launch_pack_llr(const void* in, void* var, int precision, int n_frames, cudaStream_t s);
+cudaError_t launch_unpack_bits(const uint32_t* words, int32_t* out, int stride, int K, int n_frames, cudaStream_t s);
+cudaError_t launch_pack_bits(const int32_t* in, uint32_t* words, int stride, int N, int n_frames, cudaStream_t s);
+
+struct DemapLaunch
+{
+    const float* sigma; // [frames]
+    const float* sym;   // [frames][2*n_sym]
+    const float* cstl;  // [2^bps][2] device
+    int n_frames;
+    int bps, n_sym;
+    int itl_cols, itl_rev;
+    int quant_dec, quant_bits; // for integer outputs
+};
+// frame-major float LLRs; deinterleave = 0 gives Modem::demodulate order, 1 gives natural order
+cudaError_t launch_demap_frames(const DemapLaunch& a, float* llr, int deinterleave, cudaStream_t s);
+// straight into the decoder's lane-interleaved var layout (natural order), quantised for integer precisions
+cudaError_t launch_demap_to_var(const DemapLaunch& a, void* var, int precision, cudaStream_t s);
+cudaError_t launch_deinterleave(const float* itl, float* nat, int n_frames, int n_sym, int itl_cols, int itl_rev,
+                                cudaStream_t s);
+cudaError_t launch_quantize(const float* in, void* out, int precision, size_t n, int dec, int bits, cudaStream_t s);
+
+struct BchDevTables
+{
+    const uint16_t* alpha_to; // [16384]
+    const int16_t* index_of;  // [16384]
+    uint16_t minpoly[BCH_NPOLY];
+    uint8_t poly_of[2 * BCH_T + 1];
+    uint16_t synd_mat[2 * BCH_T + 1][GF_M];
+};
+struct BchLaunch
+{
+    uint32_t* words;  // [groups][stride] bit-sliced received word, natural order; corrected in place
+    int stride;
+    uint32_t* rem;    // [groups][BCH_NPOLY][14] scratch: remainders mod the minimal polynomials
+    uint32_t* nz;     // [groups] scratch: bit f set if frame f has a non-zero syndrome
+    int8_t* cwd;      // [frames] or null
+    unsigned long long* stats;
+    int n_frames, n_groups;
+    int N, K;         // shortened BCH length and payload
+};
+cudaError_t launch_bch_decode(const BchLaunch& a, const BchDevTables& t, cudaStream_t s);
+} // namespace dvbs2

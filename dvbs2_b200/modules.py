@@ -1,0 +1,223 @@
+"""Host-side mirror of the AFF3CT/StreamPU module surface for the decode chain, on top of the C ABI.
+
+Same task names, argument order and meaning as the reference modules they stand in for (citations relative to the
+reference tree):
+  Modem_DVBS2_cuda.demodulate(CP, Y_N1, Y_N2)         <- aff3ct::module::Modem::demodulate          (Modem.hxx:222-240)
+  Interleaver_DVBS2_cuda.deinterleave(itl, nat)        <- aff3ct::module::Interleaver::deinterleave  (Interleaver.hxx:228-258)
+  Decoder_LDPC_DVBS2_cuda.decode_siho(Y_N, CWD, V_K)   <- aff3ct::module::Decoder_SIHO::decode_siho  (Decoder_SIHO.hxx:57-79)
+  Decoder_BCH_DVBS2_cuda.decode_hiho(Y_N, CWD, V_K)    <- aff3ct::module::Decoder_HIHO::decode_hiho  (Decoder_HIHO.hxx:42-63)
+  Decoder_chain_DVBS2_cuda.demodulate_decode(...)      <- the four tasks bound as in mains/TX_RX_BB/main.cpp:87-91
+Like a StreamPU task with set_single_wave(true) (Module.cpp:88-108) every call processes the whole -F batch at once:
+buffers are frame-major [n_frames][elements]; a wrong length raises ValueError (the reference throws
+spu::tools::length_error), a CUDA failure raises capi.Dvbs2CudaError (the reference throws runtime_error).
+The C++ twins that really derive from aff3ct::module::* live in module/ (see INTEGRATION.md).
+
+Host buffers are numpy arrays; the *_dev methods take torch CUDA tensors and run asynchronously on the handle's stream.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+N_LDPC = capi.N_LDPC
+
+
+def _np_ptr(a, dtype, n_elem, name):
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+        raise ValueError("'%s' must be a C-contiguous numpy array of %s" % (name, np.dtype(dtype).name))
+    if a.size != n_elem:
+        raise ValueError("'%s.size()' has to be equal to %d ('%s.size()' = %d)" % (name, n_elem, name, a.size))
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dev_ptr(t, dtype_name, n_elem, name):
+    import torch
+
+    want = {"float32": torch.float32, "int32": torch.int32, "int16": torch.int16, "int8": torch.int8}[dtype_name]
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == want and t.is_contiguous()):
+        raise ValueError("'%s' must be a contiguous CUDA tensor of %s" % (name, dtype_name))
+    if t.numel() != n_elem:
+        raise ValueError("'%s.numel()' has to be equal to %d (is %d)" % (name, n_elem, t.numel()))
+    return C.c_void_p(t.data_ptr())
+
+
+class Handle:
+    """One libdvbs2_cuda handle = one device + stream + device buffers (one per module clone, not thread-safe)."""
+
+    def __init__(self, modcod="QPSK-S_8/9", n_ite=10, norm=1.0, precision="f32", early_stop=True, n_frames=1024,
+                 device=0, quant_bits=6, quant_dec=2):
+        self.lib = capi.load()
+        if modcod not in capi.MODCOD:
+            raise ValueError(str(modcod) + " mod-cod scheme not supported.")  # DVBS2.cpp:319
+        cfg = capi.Cfg()
+        self.lib.dvbs2_cuda_default_cfg(C.byref(cfg))
+        cfg.modcod = capi.MODCOD[modcod]
+        cfg.n_ite, cfg.norm, cfg.precision = int(n_ite), float(norm), capi.PREC[precision]
+        cfg.early_stop, cfg.max_frames, cfg.device = int(bool(early_stop)), int(n_frames), int(device)
+        cfg.quant_bits, cfg.quant_dec = int(quant_bits), int(quant_dec)
+        self.modcod, self.precision, self.device = modcod, precision, device
+        self._h = C.c_void_p()
+        rc = self.lib.dvbs2_cuda_create(C.byref(cfg), C.byref(self._h))
+        if rc != capi.OK:
+            self._h = C.c_void_p()
+            raise capi.Dvbs2CudaError(rc, capi.strerror(rc))
+        info = capi.Info()
+        self.lib.dvbs2_cuda_get_info(self._h, C.byref(info))
+        self.info = {n: getattr(info, n) for n, _ in capi.Info._fields_}
+        self.llr_dtype = {"f32": np.float32, "i16": np.int16, "i8": np.int8}[precision]
+
+    def check(self, rc):
+        if rc != capi.OK:
+            msg = capi.strerror(rc)
+            if rc == capi.ERR_CUDA:
+                msg += ": " + self.lib.dvbs2_cuda_last_error(self._h).decode()
+            raise capi.Dvbs2CudaError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.dvbs2_cuda_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def sync(self):
+        self.check(self.lib.dvbs2_cuda_sync(self._h))
+
+    def stream(self):
+        return self.lib.dvbs2_cuda_stream(self._h)
+
+    def stats(self):
+        st = capi.Stats()
+        self.check(self.lib.dvbs2_cuda_get_stats(self._h, C.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in capi.Stats._fields_}
+
+    def reset_stats(self):
+        self.check(self.lib.dvbs2_cuda_reset_stats(self._h))
+
+    def host_register(self, arr):
+        self.check(self.lib.dvbs2_cuda_host_register(self._h, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+
+    def host_unregister(self, arr):
+        self.check(self.lib.dvbs2_cuda_host_unregister(self._h, arr.ctypes.data_as(C.c_void_p)))
+
+
+class _Module:
+    """Common part: a (possibly shared) Handle and the StreamPU-style n_frames bookkeeping."""
+
+    def __init__(self, handle, n_frames):
+        self.h = handle
+        self.n_frames = 0
+        self.set_n_frames(n_frames)
+
+    def set_n_frames(self, n_frames):  # Module::set_n_frames (Module.cpp:43-86)
+        if n_frames <= 0:
+            raise ValueError("'n_frames' has to be greater than 0 ('n_frames' = %d)." % n_frames)
+        if n_frames > self.h.info["max_frames"]:
+            raise ValueError("'n_frames' exceeds the handle's max_frames (%d > %d)" % (n_frames, self.h.info["max_frames"]))
+        self.n_frames = int(n_frames)
+
+    def get_n_frames(self):
+        return self.n_frames
+
+
+class Modem_DVBS2_cuda(_Module):
+    """Soft demapper of the handle's MODCOD.  demodulate: CP[F] (sigma), Y_N1[F][2*n_sym] -> Y_N2[F][16200]."""
+
+    def __init__(self, handle, n_frames=1):
+        super().__init__(handle, n_frames)
+        self.N = N_LDPC
+        self.N_fil = 2 * handle.info["n_sym"]
+
+    def demodulate(self, CP, Y_N1, Y_N2):
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_demodulate(h._h, _np_ptr(CP, np.float32, F, "CP"),
+                                            _np_ptr(Y_N1, np.float32, F * self.N_fil, "Y_N1"),
+                                            _np_ptr(Y_N2, np.float32, F * self.N, "Y_N2"), F))
+
+    def demodulate_dev(self, CP, Y_N1, Y_N2, deinterleave=False):
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_demodulate_dev(h._h, _dev_ptr(CP, "float32", F, "CP"),
+                                                _dev_ptr(Y_N1, "float32", F * self.N_fil, "Y_N1"),
+                                                _dev_ptr(Y_N2, "float32", F * self.N, "Y_N2"), int(deinterleave), F))
+
+
+class Interleaver_DVBS2_cuda(_Module):
+    """Column-row deinterleaver of the handle's MODCOD (identity for QPSK)."""
+
+    def deinterleave(self, itl, nat):
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_deinterleave(h._h, _np_ptr(itl, np.float32, F * N_LDPC, "itl"),
+                                              _np_ptr(nat, np.float32, F * N_LDPC, "nat"), F))
+
+
+class Decoder_LDPC_DVBS2_cuda(_Module):
+    """Horizontal-layered (N)MS decoder.  decode_siho: Y_N[F][16200] -> CWD[F] (int8), V_K[F][K] (int32)."""
+
+    def __init__(self, handle, n_frames=1):
+        super().__init__(handle, n_frames)
+        self.K, self.N = handle.info["K_ldpc"], N_LDPC
+
+    def decode_siho(self, Y_N, CWD, V_K, n_iter=None):
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_ldpc_decode_siho(
+            h._h, _np_ptr(Y_N, h.llr_dtype, F * self.N, "Y_N"), _np_ptr(CWD, np.int8, F, "CWD"),
+            _np_ptr(V_K, np.int32, F * self.K, "V_K"),
+            None if n_iter is None else _np_ptr(n_iter, np.int32, F, "n_iter"), F))
+        return int(np.count_nonzero(CWD == 0) != 0)  # task status: 0 = every frame is a codeword
+
+    def decode_siho_dev(self, Y_N, CWD, V_K, n_iter=None):
+        F, h = self.n_frames, self.h
+        name = {"f32": "float32", "i16": "int16", "i8": "int8"}[h.precision]
+        h.check(h.lib.dvbs2_cuda_ldpc_decode_siho_dev(
+            h._h, _dev_ptr(Y_N, name, F * self.N, "Y_N"), _dev_ptr(CWD, "int8", F, "CWD"),
+            _dev_ptr(V_K, "int32", F * self.K, "V_K"),
+            None if n_iter is None else _dev_ptr(n_iter, "int32", F, "n_iter"), F))
+
+
+class Decoder_BCH_DVBS2_cuda(_Module):
+    """BCH t = 12 hard decoder, DVB-S2 bit order.  decode_hiho: Y_N[F][N_bch] -> CWD[F], V_K[F][K_bch]."""
+
+    def __init__(self, handle, n_frames=1):
+        super().__init__(handle, n_frames)
+        self.K, self.N = handle.info["K_bch"], handle.info["N_bch"]
+
+    def decode_hiho(self, Y_N, CWD, V_K):
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_bch_decode_hiho(h._h, _np_ptr(Y_N, np.int32, F * self.N, "Y_N"),
+                                                 _np_ptr(CWD, np.int8, F, "CWD"),
+                                                 _np_ptr(V_K, np.int32, F * self.K, "V_K"), F))
+        return int(np.count_nonzero(CWD == 0) != 0)
+
+    def decode_hiho_dev(self, Y_N, CWD, V_K):
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_bch_decode_hiho_dev(h._h, _dev_ptr(Y_N, "int32", F * self.N, "Y_N"),
+                                                     _dev_ptr(CWD, "int8", F, "CWD"),
+                                                     _dev_ptr(V_K, "int32", F * self.K, "V_K"), F))
+
+
+class Decoder_chain_DVBS2_cuda(_Module):
+    """Fused stage: demodulate -> deinterleave -> (quantize) -> LDPC decode_siho -> BCH decode_hiho on the device."""
+
+    def __init__(self, handle, n_frames=1):
+        super().__init__(handle, n_frames)
+        self.K = handle.info["K_bch"]
+        self.N_fil = 2 * handle.info["n_sym"]
+
+    def demodulate_decode(self, CP, Y_N1, CWD_ldpc, CWD_bch, V_K, n_iter=None):
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_chain(
+            h._h, _np_ptr(CP, np.float32, F, "CP"), _np_ptr(Y_N1, np.float32, F * self.N_fil, "Y_N1"),
+            None if CWD_ldpc is None else _np_ptr(CWD_ldpc, np.int8, F, "CWD_ldpc"),
+            None if CWD_bch is None else _np_ptr(CWD_bch, np.int8, F, "CWD_bch"),
+            _np_ptr(V_K, np.int32, F * self.K, "V_K"),
+            None if n_iter is None else _np_ptr(n_iter, np.int32, F, "n_iter"), F))
+
+    def demodulate_decode_dev(self, CP, Y_N1, CWD_ldpc, CWD_bch, V_K, n_iter=None):
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_chain_dev(
+            h._h, _dev_ptr(CP, "float32", F, "CP"), _dev_ptr(Y_N1, "float32", F * self.N_fil, "Y_N1"),
+            None if CWD_ldpc is None else _dev_ptr(CWD_ldpc, "int8", F, "CWD_ldpc"),
+            None if CWD_bch is None else _dev_ptr(CWD_bch, "int8", F, "CWD_bch"),
+            _dev_ptr(V_K, "int32", F * self.K, "V_K"),
+            None if n_iter is None else _dev_ptr(n_iter, "int32", F, "n_iter"), F))

@@ -1,0 +1,150 @@
+/*
+ * libdvbs2_cuda — C ABI of the B200-native DVB-S2 baseband decode chain
+ * (soft demapper -> deinterleaver -> horizontal-layered (N)MS LDPC decoder -> BCH t=12 hard decoder).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry point replaces the codelet
+ * body of one AFF3CT/StreamPU task of aff3ct/dvbs2 (citations relative to the reference tree; A/ = lib/aff3ct,
+ * D/ = src, S/ = lib/streampu):
+ *
+ *   dvbs2_cuda_demodulate        <- Modem<B,R,Q>::demodulate codelet, A/include/Module/Modem/Modem.hxx:222-240
+ *                                   (-> Modem_generic_fast::_demodulate_complex, .../Generic/Modem_generic_fast.hxx:193-225)
+ *   dvbs2_cuda_deinterleave      <- Interleaver<D,T>::deinterleave, A/include/Module/Interleaver/Interleaver.hxx:228-258
+ *   dvbs2_cuda_ldpc_decode_siho  <- Decoder_SIHO<B,R>::decode_siho codelet, A/include/Module/Decoder/Decoder_SIHO.hxx:57-79
+ *                                   (-> Decoder_LDPC_BP_horizontal_layered<...,Update_rule_NMS>::_decode_siho,
+ *                                    A/include/Module/Decoder/LDPC/BP/Horizontal_layered/Decoder_LDPC_BP_horizontal_layered.hxx:89-123)
+ *   dvbs2_cuda_bch_decode_hiho   <- Decoder_HIHO<B>::decode_hiho codelet, A/include/Module/Decoder/Decoder_HIHO.hxx:42-63
+ *                                   (-> Decoder_BCH_DVBS2::_decode_hiho, D/common/Module/Decoder_BCH_DVBS2/Decoder_BCH_DVBS2.cpp:28-40)
+ *   dvbs2_cuda_chain             <- the four tasks above bound back to back as in D/mains/TX_RX_BB/main.cpp:87-91
+ *                                   (pipeline stage 6 of D/mains/RX/main_8-sta.cpp:291-296), fused on the device
+ *   dvbs2_cuda_quantize          <- Quantizer_pow2::_process, A/src/Module/Quantizer/Pow2/Quantizer_pow2.cpp:184-190
+ *
+ * Conventions (same as the reference sockets): buffers are frame-major and contiguous,
+ * LLR/symbols/sigma are float, bits are int32_t (0/1), CWD is int8_t (1 = decoder holds a valid codeword).
+ * Every function returns DVBS2_OK (0) or a negative dvbs2_status; nothing throws across the ABI.
+ * One handle = one device + one stream + its device buffers; a handle is NOT thread-safe (one per module clone).
+ * There is no CPU fallback: if no CUDA device is usable, dvbs2_cuda_create fails with DVBS2_ERR_CUDA.
+ */
+#ifndef DVBS2_CUDA_H
+#define DVBS2_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#define DVBS2_N_LDPC 16200 /* D/common/Factory/DVBS2/DVBS2.hpp:49 — short FECFRAME */
+
+    typedef enum
+    {
+        DVBS2_OK = 0,
+        DVBS2_ERR_INVALID = -1,   /* bad argument / unsupported configuration                */
+        DVBS2_ERR_CUDA = -2,      /* CUDA runtime error (see dvbs2_cuda_last_error)          */
+        DVBS2_ERR_TOO_MANY = -3,  /* n_frames > cfg.max_frames                               */
+        DVBS2_ERR_NOMEM = -4      /* device or host allocation failed                        */
+    } dvbs2_status;
+
+    /* --mod-cod values of D/common/Factory/DVBS2/DVBS2.cpp:287-317 */
+    typedef enum
+    {
+        DVBS2_QPSK_S_8_9 = 0,
+        DVBS2_QPSK_S_3_5 = 1,
+        DVBS2_8PSK_S_3_5 = 2,
+        DVBS2_8PSK_S_8_9 = 3,
+        DVBS2_16APSK_S_8_9 = 4
+    } dvbs2_modcod;
+
+    /* arithmetic of the LDPC decoder: AFF3CT's R type (A/include/Tools/types.h:11-49) */
+    typedef enum
+    {
+        DVBS2_PREC_F32 = 0, /* R = float   (what the dvbs2 binaries run)                                  */
+        DVBS2_PREC_I16 = 1, /* R = int16_t (AFF3CT Q_16 fixed point, sequential wrap semantics)           */
+        DVBS2_PREC_I8 = 2   /* R = int8_t  (AFF3CT Q_8, sequential wrap semantics)         */
+    } dvbs2_prec;
+
+    typedef struct
+    {
+        int modcod;      /* dvbs2_modcod                                                                   */
+        int n_ite;       /* --dec-ite  (DVBS2.cpp:135), >= 1                                               */
+        float norm;      /* NMS normalisation factor; dvbs2 runs 1.0; ints: k/8 only           */
+        int precision;   /* dvbs2_prec                                                                     */
+        int early_stop;  /* 1 = syndrome early termination per frame (enable_syndrome, depth 1)            */
+        int max_frames;  /* largest -F this handle will be asked to process in one call                    */
+        int device;      /* CUDA device ordinal                                                            */
+        int quant_bits;  /* Quantizer_pow2 saturation_pos (AFF3CT default 6), used by int precisions       */
+        int quant_dec;   /* Quantizer_pow2 fixed_point_pos (AFF3CT default 2)                              */
+        int reserved[7]; /* must be 0                                                                      */
+    } dvbs2_cuda_cfg;
+
+    typedef struct
+    {
+        int K_bch, N_bch, K_ldpc, N_ldpc, bps, n_sym; /* code/modulation sizes of cfg.modcod               */
+        int M_ldpc, E_ldpc;                           /* checks / edges of H                               */
+        int max_frames;
+    } dvbs2_cuda_info;
+
+    typedef struct
+    {
+        uint64_t frames;          /* frames decoded by LDPC since create/reset                              */
+        uint64_t ldpc_iterations; /* sum over frames of iterations executed                                 */
+        uint64_t ldpc_failures;   /* frames whose syndrome was non-zero after the last iteration            */
+        uint64_t bch_nonzero;     /* frames entering Berlekamp (non-zero BCH syndrome)                      */
+        uint64_t bch_failures;    /* frames BCH could not correct                                           */
+        uint64_t kernel_launches; /* kernels launched by this handle                                        */
+    } dvbs2_cuda_stats;
+
+    typedef struct dvbs2_cuda_handle dvbs2_cuda_handle;
+
+    void dvbs2_cuda_default_cfg(dvbs2_cuda_cfg* cfg); /* QPSK-S_8/9, 10 it, norm 1.0, f32, early stop, 1024 frames */
+    int dvbs2_cuda_create(const dvbs2_cuda_cfg* cfg, dvbs2_cuda_handle** out);
+    int dvbs2_cuda_destroy(dvbs2_cuda_handle* h);
+    int dvbs2_cuda_get_info(const dvbs2_cuda_handle* h, dvbs2_cuda_info* info);
+    int dvbs2_cuda_get_stats(dvbs2_cuda_handle* h, dvbs2_cuda_stats* stats); /* synchronises the stream */
+    int dvbs2_cuda_reset_stats(dvbs2_cuda_handle* h);
+    const char* dvbs2_cuda_strerror(int status);
+    const char* dvbs2_cuda_last_error(const dvbs2_cuda_handle* h); /* text of the last CUDA failure */
+    int dvbs2_cuda_device_count(void);
+
+    /* ---- host-buffer entry points (what the StreamPU modules call; H2D/D2H inside, synchronous on return) ------- */
+
+    /* CP[F] = sigma per frame; Y_N1[F][2*n_sym] interleaved I/Q; Y_N2[F][16200] LLRs in transmitted (interleaved)
+     * bit order, exactly Modem::demodulate.  Log-MAP (max*) over the MODCOD's constellation. */
+    int dvbs2_cuda_demodulate(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, float* Y_N2, int n_frames);
+    /* nat[f][i] = itl[f][pi_inv[i]] (identity for QPSK) */
+    int dvbs2_cuda_deinterleave(dvbs2_cuda_handle* h, const float* itl, float* nat, int n_frames);
+    /* Y_N[F][16200]: float (F32) / int16_t (I16) / int8_t (I8) LLRs in natural order; CWD[F]; V_K[F][K_ldpc].
+     * n_iter (optional, may be NULL) receives the iterations executed per frame. */
+    int dvbs2_cuda_ldpc_decode_siho(dvbs2_cuda_handle* h, const void* Y_N, int8_t* CWD, int32_t* V_K, int32_t* n_iter,
+                                    int n_frames);
+    /* Y_N[F][N_bch] hard bits; CWD[F]; V_K[F][K_bch] */
+    int dvbs2_cuda_bch_decode_hiho(dvbs2_cuda_handle* h, const int32_t* Y_N, int8_t* CWD, int32_t* V_K, int n_frames);
+    /* float LLR -> fixed point with cfg.quant_dec / cfg.quant_bits; out is int16_t or int8_t per cfg.precision */
+    int dvbs2_cuda_quantize(dvbs2_cuda_handle* h, const float* in, void* out, size_t n);
+    /* Fused stage: demodulate -> deinterleave -> (quantize) -> LDPC -> BCH; LLRs and LDPC bits never leave the device.
+     * CWD_ldpc / CWD_bch / n_iter may be NULL.  Copies are chunked and overlapped with compute; pass pinned memory
+     * (dvbs2_cuda_host_register) for full PCIe rate. */
+    int dvbs2_cuda_chain(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
+                         int32_t* V_K, int32_t* n_iter, int n_frames);
+
+    /* pin / unpin a caller-owned host buffer (StreamPU socket buffers are stable after binding) */
+    int dvbs2_cuda_host_register(dvbs2_cuda_handle* h, void* ptr, size_t bytes);
+    int dvbs2_cuda_host_unregister(dvbs2_cuda_handle* h, void* ptr);
+
+    /* ---- device-buffer entry points (asynchronous on the handle's stream; for benchmarks and device-resident use) -- */
+    void* dvbs2_cuda_stream(dvbs2_cuda_handle* h); /* cudaStream_t */
+    int dvbs2_cuda_sync(dvbs2_cuda_handle* h);
+    int dvbs2_cuda_demodulate_dev(dvbs2_cuda_handle* h, const float* d_CP, const float* d_Y_N1, float* d_Y_N2,
+                                  int deinterleave, int n_frames);
+    int dvbs2_cuda_ldpc_decode_siho_dev(dvbs2_cuda_handle* h, const void* d_Y_N, int8_t* d_CWD, int32_t* d_V_K,
+                                        int32_t* d_n_iter, int n_frames);
+    int dvbs2_cuda_bch_decode_hiho_dev(dvbs2_cuda_handle* h, const int32_t* d_Y_N, int8_t* d_CWD, int32_t* d_V_K,
+                                       int n_frames);
+    int dvbs2_cuda_chain_dev(dvbs2_cuda_handle* h, const float* d_CP, const float* d_Y_N1, int8_t* d_CWD_ldpc,
+                             int8_t* d_CWD_bch, int32_t* d_V_K, int32_t* d_n_iter, int n_frames);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

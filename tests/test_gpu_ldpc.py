@@ -1,0 +1,112 @@
+"""GPU parity: LDPC decoder through the C ABI vs the CPU oracle on identical LLRs (bit-exact, all precisions)."""
+import numpy as np
+import pytest
+
+from oracle.oracle import MODCODS, N_LDPC, synth_frames
+
+pytestmark = pytest.mark.gpu
+
+
+def _llrs(oracle, modcod, F, ebn0, seed=1):
+    s = synth_frames(oracle, modcod, F, ebn0, seed=seed)
+    mc = MODCODS[modcod]
+    llr = oracle.demodulate(mc["bps"], s["sigma"], s["rx"])
+    _, inv = oracle.itl_lut(mc["bps"], mc["itl"])
+    return np.ascontiguousarray(llr[:, inv]), s
+
+
+def _decode(modcod, Y, prec="f32", n_ite=10, norm=1.0, early_stop=True):
+    from dvbs2_b200 import Decoder_LDPC_DVBS2_cuda, Handle
+
+    F = Y.shape[0]
+    h = Handle(modcod=modcod, n_ite=n_ite, norm=norm, precision=prec, early_stop=early_stop, n_frames=F)
+    dec = Decoder_LDPC_DVBS2_cuda(h, F)
+    V = np.zeros((F, dec.K), np.int32)
+    cwd = np.zeros(F, np.int8)
+    nit = np.zeros(F, np.int32)
+    dec.decode_siho(Y, cwd, V, nit)
+    st = h.stats()
+    h.close()
+    return V, cwd, nit, st
+
+
+@pytest.mark.parametrize("modcod,ebn0", [("QPSK-S_8/9", 3.9), ("QPSK-S_3/5", 2.3), ("8PSK-S_3/5", 4.0),
+                                         ("8PSK-S_8/9", 6.7), ("16APSK-S_8/9", 7.7)])
+def test_f32_bit_exact_all_modcods(oracle, modcod, ebn0):
+    Y, _ = _llrs(oracle, modcod, 96, ebn0)
+    K = MODCODS[modcod]["N_bch"]
+    V, cwd, nit, st = _decode(modcod, Y)
+    Vo, co, no = oracle.ldpc_decode(K, Y)
+    assert np.array_equal(nit, no)
+    assert np.array_equal(cwd, co)
+    assert np.array_equal(V, Vo)
+    assert st["frames"] == 96 and st["ldpc_iterations"] == int(no.sum()) and st["ldpc_failures"] == int((co == 0).sum())
+
+
+@pytest.mark.parametrize("F", [1, 31, 32, 33, 70])
+def test_ragged_batches(oracle, F):
+    Y, _ = _llrs(oracle, "QPSK-S_8/9", F, 4.0, seed=F)
+    V, cwd, nit, _ = _decode("QPSK-S_8/9", Y)
+    Vo, co, no = oracle.ldpc_decode(14400, Y)
+    assert np.array_equal(V, Vo) and np.array_equal(cwd, co) and np.array_equal(nit, no)
+
+
+@pytest.mark.parametrize("prec,dec,bits", [("i16", 2, 6), ("i8", 2, 6), ("i8", 1, 6), ("i16", 3, 8)])
+@pytest.mark.parametrize("modcod,ebn0", [("QPSK-S_8/9", 4.0), ("8PSK-S_3/5", 4.0)])
+def test_fixed_point_bit_exact(oracle, prec, dec, bits, modcod, ebn0):
+    Y, _ = _llrs(oracle, modcod, 64, ebn0)
+    q = oracle.quantize(Y, dec, bits, prec)
+    K = MODCODS[modcod]["N_bch"]
+    V, cwd, nit, _ = _decode(modcod, q, prec=prec)
+    Vo, co, no = oracle.ldpc_decode(K, q, prec=prec)
+    assert np.array_equal(nit, no) and np.array_equal(cwd, co) and np.array_equal(V, Vo)
+
+
+@pytest.mark.parametrize("norm", [0.75, 0.875, 0.5])
+@pytest.mark.parametrize("prec", ["f32", "i16"])
+def test_normalisation_factors(oracle, norm, prec):
+    Y, _ = _llrs(oracle, "QPSK-S_8/9", 64, 3.9)
+    if prec != "f32":
+        Y = oracle.quantize(Y, 2, 6, prec)
+    V, cwd, nit, _ = _decode("QPSK-S_8/9", Y, prec=prec, norm=norm)
+    Vo, co, no = oracle.ldpc_decode(14400, Y, norm=norm, prec=prec)
+    assert np.array_equal(nit, no) and np.array_equal(cwd, co) and np.array_equal(V, Vo)
+
+
+def test_no_early_stop_and_iteration_counts(oracle):
+    Y, _ = _llrs(oracle, "QPSK-S_8/9", 64, 4.2)
+    V, cwd, nit, _ = _decode("QPSK-S_8/9", Y, n_ite=5, early_stop=False)
+    Vo, co, no = oracle.ldpc_decode(14400, Y, n_ite=5, early_stop=False)
+    assert (nit == 5).all() and np.array_equal(V, Vo) and np.array_equal(cwd, co)
+    for n_ite in (1, 3, 20):
+        V, cwd, nit, _ = _decode("QPSK-S_8/9", Y, n_ite=n_ite)
+        Vo, co, no = oracle.ldpc_decode(14400, Y, n_ite=n_ite)
+        assert np.array_equal(nit, no) and np.array_equal(V, Vo) and np.array_equal(cwd, co)
+
+
+def test_extreme_inputs(oracle):
+    """all-zero LLRs, huge LLRs, noiseless codewords, all-erased parity: no NaN surprises, still bit-exact."""
+    rng = np.random.default_rng(3)
+    s = synth_frames(oracle, "QPSK-S_8/9", 8, 100.0)
+    clean = (1.0 - 2.0 * s["ldpc"].astype(np.float32)) * 8.0
+    Y = np.stack([np.zeros(N_LDPC, np.float32), clean[1] * 1e30, clean[2], clean[3] * 1e-30,
+                  np.where(np.arange(N_LDPC) >= 14400, 0.0, clean[4]).astype(np.float32),
+                  rng.standard_normal(N_LDPC).astype(np.float32), -clean[6], clean[7]])
+    Y = np.ascontiguousarray(Y, np.float32)
+    V, cwd, nit, _ = _decode("QPSK-S_8/9", Y)
+    Vo, co, no = oracle.ldpc_decode(14400, Y)
+    assert np.array_equal(nit, no) and np.array_equal(cwd, co) and np.array_equal(V, Vo)
+
+
+def test_large_batch_round_trip(oracle):
+    """Size-independent property at a size the oracle would not finish quickly: noiseless-ish codewords decode to the
+    transmitted bits in one iteration, for every frame of a multi-thousand batch."""
+    s = synth_frames(oracle, "QPSK-S_8/9", 16, 12.0)
+    mc = MODCODS["QPSK-S_8/9"]
+    llr = oracle.demodulate(2, s["sigma"], s["rx"])
+    reps = 160  # 2560 frames
+    Y = np.ascontiguousarray(np.tile(llr, (reps, 1)))
+    V, cwd, nit, st = _decode("QPSK-S_8/9", Y)
+    assert (cwd == 1).all() and (nit == 1).all()
+    assert np.array_equal(V, np.tile(s["bch"], (reps, 1)))
+    assert st["frames"] == 16 * reps
