@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the DVB-S2 baseband decode chain (demap -> LDPC NMS-10 -> BCH) on B200 — driver contract.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload qpsk89|qpsk35|8psk35|8psk89|16apsk89]
+
+One "step" = one pass of the fused chain (dvbs2_cuda_chain_dev) over one batch of F synthetic AWGN frames per GPU.
+`value`  = info Mbit/s (K_bch * frames / time, the reference's throughput definition, D/mains/TX_RX_BB/main.cpp:130) with
+           the received symbols already resident in HBM; whole-job aggregate over all ranks (frames shard by batch, no
+           collective on the data path; NCCL only reduces the time and the FER counters).
+`e2e`    = the same metric through the host-buffer C-ABI call (dvbs2_cuda_chain) with pinned HOST buffers: H2D of the
+           symbols and D2H of the int32 bits inside the timed region.
+`roofline` = the LDPC kernel (dominant), algorithmic bytes per frame from SURVEY.md §8(d) / DESIGN.md §5.
+`cpu_baseline` = the compiled reference chain (oracle/_ref, AVX-512 ONMS_inter -F 16 + Modem_generic_fast + BCH_std) on
+           this box's host cores, bounded sample; `--impl reference` times just that.
+Multi-GPU: launched by torchrun (one rank per GPU); barrier + synchronize around the timed region, MAX over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json metric/config[0]: QPSK-S_8/9 at Eb/N0 4.0 dB;  config[1]: QPSK-S_3/5 at the NMS-10 waterfall
+    "qpsk89": dict(modcod="QPSK-S_8/9", ebn0=4.0),
+    "qpsk35": dict(modcod="QPSK-S_3/5", ebn0=2.2),
+    "8psk35": dict(modcod="8PSK-S_3/5", ebn0=3.9),
+    "8psk89": dict(modcod="8PSK-S_8/9", ebn0=7.5),
+    "16apsk89": dict(modcod="16APSK-S_8/9", ebn0=7.6),
+}
+N_LDPC = 16200
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--workload", default="qpsk89", choices=sorted(WORKLOADS))
+    p.add_argument("--ebn0", type=float, default=None)
+    p.add_argument("--prec", default="f32", choices=["f32", "i16", "i8"])
+    p.add_argument("--ite", type=int, default=10)
+    p.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: 148 SMs x 16 warps x 32)")
+    p.add_argument("--e2e-frames", type=int, default=32768)
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--cpu-threads", type=int, default=0)
+    return p.parse_args()
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        for k in ("hbm_gbs", "hbm_gb_s", "hbm_copy_gbs"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.1 <= t <= t1 + 0.3 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(int(float(r[0])) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(rows[0][1])), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(pw) if pw else None}
+
+
+def host_threads(args):
+    if args.cpu_threads > 0:
+        return args.cpu_threads
+    n = os.cpu_count() or 1
+    try:  # every reference BCH clone allocates a 1.07 GB table
+        import psutil
+
+        n = max(1, min(n, int(psutil.virtual_memory().available * 0.6 / 1.2e9)))
+    except Exception:
+        pass
+    return n
+
+
+def cpu_reference_run(modcod, ite, sigma, sym, seconds, threads):
+    """Frames/s of the compiled reference chain (demodulate + deinterleave + ONMS_inter LDPC + BCH) on `threads` cores."""
+    import numpy as np
+
+    from oracle.oracle import N_LDPC as N, Ref
+
+    if not Ref.available():
+        return None
+    r = Ref()
+    F = sym.shape[0]
+    llr = np.zeros((F, N), np.float32)
+    fps, done = r.bench_chain(modcod, ite, threads, seconds, 7, sigma, sym, llr)
+    r.close()
+    return fps, done
+
+
+def host_sample(modcod, ebn0, n_frames, seed=0xD5B52):
+    """Small host batch of the bench workload for the CPU arm: random payloads through the TX chain + AWGN (oracle's
+    synth_frames — random codewords matter on the CPU: the reference BCH skips zero bits in its syndrome loop)."""
+    from oracle.oracle import Oracle, synth_frames
+
+    s = synth_frames(Oracle(), modcod, n_frames, ebn0, seed=seed)
+    return s["sigma"], s["rx"]
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, bounded sample/step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from dvbs2_b200 import synth
+
+    wl = WORKLOADS[args.workload]
+    modcod, ebn0 = wl["modcod"], wl["ebn0"] if args.ebn0 is None else args.ebn0
+    K_bch = synth.MODCODS[modcod]["K_bch"]
+    try:
+        from oracle.oracle import Ref
+
+        ok = Ref.available()
+    except Exception as e:  # noqa: BLE001
+        ok = False
+    if not ok:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libdvbs2_ref.so not built on this host"}))
+        return
+    threads = host_threads(args)
+    sig, rx = host_sample(modcod, ebn0, 512)
+    n_calls = args.steps + args.warmup
+    sec = max(0.5, min(4.0, 100.0 / max(1, n_calls)))
+    fps = []
+    for i in range(n_calls):
+        r = cpu_reference_run(modcod, args.ite, sig, rx, sec, threads)
+        if i >= args.warmup:
+            fps.append(r[0])
+    v = K_bch * (sum(fps) / len(fps)) / 1e6
+    sample = "%d x %.1f s of the chain over 512 frames cycling, %d threads x ONMS_inter -F 16" % (len(fps), sec, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": "info Mbit/s, %s NMS %d-iter decode chain (demap+LDPC+BCH)" % (modcod, args.ite),
+        "value": round(v, 3), "unit": "Mbit/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (all-zero codeword + AWGN, numpy)",
+        "config": {"workload": "%s Eb/N0 %.2f dB NMS norm 1.0 %d it, early stop" % (modcod, ebn0, args.ite)},
+        "cpu_baseline": {"value": round(v, 3), "unit": "Mbit/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": round(v, 3), "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from dvbs2_b200 import Decoder_chain_DVBS2_cuda, Handle, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+
+    def reduce_(x, op):
+        t = torch.tensor(x, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return t.tolist()
+
+    wl = WORKLOADS[args.workload]
+    modcod, ebn0 = wl["modcod"], wl["ebn0"] if args.ebn0 is None else args.ebn0
+    mc = synth.MODCODS[modcod]
+    K_bch, N_bch, bps = mc["K_bch"], mc["N_bch"], mc["bps"]
+    n_sym = N_LDPC // bps
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    F = args.frames if args.frames > 0 else sms * 16 * 32
+    NB = 2  # input batches rotated between steps (each is far larger than the 126 MB L2)
+
+    h = Handle(modcod=modcod, n_ite=args.ite, norm=1.0, precision=args.prec, early_stop=True, n_frames=F, device=local)
+    chain = Decoder_chain_DVBS2_cuda(h, F)
+    batches = [synth.awgn_zero_codeword(modcod, F, ebn0, dev, seed=0xD5B52 + 1000 * rank + b) for b in range(NB)]
+    V = torch.zeros((F, K_bch), dtype=torch.int32, device=dev)
+    c1 = torch.zeros(F, dtype=torch.int8, device=dev)
+    c2 = torch.zeros(F, dtype=torch.int8, device=dev)
+    nit = torch.zeros(F, dtype=torch.int32, device=dev)
+    ext = torch.cuda.ExternalStream(h.stream(), device=dev)
+
+    def step(i):
+        sig, rx = batches[i % NB]
+        chain.demodulate_decode_dev(sig, rx, c1, c2, V, nit)
+
+    torch.cuda.synchronize()
+    for i in range(args.warmup):
+        step(i)
+    h.sync()
+    h.reset_stats()
+    h.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    with torch.cuda.stream(ext):
+        e0.record()
+    for i in range(args.steps):
+        step(i)
+    with torch.cuda.stream(ext):
+        e1.record()
+    h.sync()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t0, t1)
+    tm = h.timers()
+    st = h.stats()
+    h.set_profiling(False)
+    ms_max = reduce_([ms], dist.ReduceOp.MAX if world > 1 else None)[0]
+    # FER / iteration counters of the timed region: NCCL sum over ranks (the Monitor_reduction replacement)
+    cnt = reduce_([st["frames"], st["ldpc_iterations"], st["ldpc_failures"], st["bch_failures"], st["bch_nonzero"]],
+                  dist.ReduceOp.SUM if world > 1 else None)
+    frames_total = F * args.steps * world
+    value = K_bch * frames_total / (ms_max * 1e-3) / 1e6
+    # all-zero codeword: every accepted frame must carry the all-zero payload
+    payload_ok = bool((V[c2 == 1] == 0).all().item())
+
+    # ---- roofline of the dominant kernel (LDPC decode), live CUDA-event time per launch
+    peak, peak_src = hbm_peak()
+    ldpc_ms = tm["ldpc_ms"] / max(1, tm["ldpc_calls"])
+    esz = {"f32": 4, "i16": 2, "i8": 1}[args.prec]
+    alg_bytes_frame = esz * N_LDPC + 4 * N_bch + 1  # compulsory I/O of decode_siho with AFF3CT socket types
+    achieved = alg_bytes_frame * F / (ldpc_ms * 1e-3) / 1e9
+    M = N_LDPC - N_bch
+    d_info = 25 if N_bch == 14400 else 9
+    E_info = M * d_info
+    it_per_frame = st["ldpc_iterations"] / max(1, st["frames"])
+    msg_bytes_frame = it_per_frame * (2 * esz * E_info + 2 * esz * M + 32 * M)  # DESIGN.md §5 message-passing traffic
+    roofline = {"bound": "hbm", "kernel": "ldpc_decode_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_frame": alg_bytes_frame, "kernel_ms": round(ldpc_ms, 4),
+                "kernel_share_of_step": round(tm["ldpc_ms"] / ms, 4),
+                "message_passing": {"bytes_per_frame": round(msg_bytes_frame), "achieved": round(msg_bytes_frame * F / (ldpc_ms * 1e-3) / 1e9, 1),
+                                    "frac": round(msg_bytes_frame * F / (ldpc_ms * 1e-3) / 1e9 / peak, 4)}}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            roofline["traffic"] = json.load(f).get(args.workload + "_" + args.prec)
+    except Exception:
+        pass
+    stage_ms = {k[:-3]: round(tm[k] / max(1, tm[k[:-3] + "_calls"]), 4) for k in tm if k.endswith("_ms") and tm[k[:-3] + "_calls"]}
+    launches = st["kernel_launches"]
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        Fe = min(F, args.e2e_frames)
+        che = Decoder_chain_DVBS2_cuda(h, Fe)
+        hs = torch.empty(Fe, dtype=torch.float32).pin_memory()
+        hx = torch.empty((Fe, 2 * n_sym), dtype=torch.float32).pin_memory()
+        hV = torch.empty((Fe, K_bch), dtype=torch.int32).pin_memory()
+        hc1, hc2 = torch.empty(Fe, dtype=torch.int8).pin_memory(), torch.empty(Fe, dtype=torch.int8).pin_memory()
+        hn = torch.empty(Fe, dtype=torch.int32).pin_memory()
+        hs.copy_(batches[0][0][:Fe])
+        hx.copy_(batches[0][1][:Fe])
+        torch.cuda.synchronize()
+        a = [t.numpy() for t in (hs, hx, hc1, hc2, hV, hn)]
+        for _ in range(max(1, min(args.warmup, 3))):
+            che.demodulate_decode(*a)
+        barrier()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            che.demodulate_decode(*a)
+        torch.cuda.synchronize()
+        w = time.perf_counter() - w0
+        w = reduce_([w], dist.ReduceOp.MAX if world > 1 else None)[0]
+        barrier()
+        e2e = {"value": round(K_bch * Fe * args.steps * world / w / 1e6, 2), "unit": "Mbit/s",
+               "h2d_bytes_per_step": int(hs.numel() * 4 + hx.numel() * 4),
+               "d2h_bytes_per_step": int(hV.numel() * 4 + 2 * Fe + hn.numel() * 4), "frames_per_step_per_gpu": Fe,
+               "ms_per_step": round(w / args.steps * 1e3, 3), "api": "dvbs2_cuda_chain (host pointers, pinned)"}
+        del hx, hV
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the compiled reference on this box's host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            threads = host_threads(args)
+            sig, rx = host_sample(modcod, ebn0, 512)
+            r = cpu_reference_run(modcod, args.ite, sig, rx, args.cpu_seconds, threads)
+            if r is not None:
+                cpu = {"value": round(K_bch * r[0] / 1e6, 3), "unit": "Mbit/s", "cores": threads, "kind": "reference",
+                       "sample": "%.0f s of demap+deinterleave+ONMS_inter(-F 16)+BCH_std over 512 frames cycling, %d frames done"
+                                 % (args.cpu_seconds, int(r[1]))}
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": "Mbit/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
+
+    if rank == 0:
+        out = {
+            "metric": "info Mbit/s, %s NMS %d-iter decode chain (demap+LDPC+BCH)" % (modcod, args.ite),
+            "value": round(value, 2), "unit": "Mbit/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.prec, "data": "synthetic (all-zero codeword + AWGN generated on device, torch.Generator)",
+            "config": {"workload": "%s Eb/N0 %.2f dB NMS norm 1.0 %d it, early stop" % (modcod, ebn0, args.ite),
+                       "frames_per_step_per_gpu": F, "sigma": round(synth.ebn0_to_sigma(modcod, ebn0), 5),
+                       "l2": "inputs %.1f GB per step >> 126 MB L2, %d batches rotated" % (F * 2 * n_sym * 4 / 1e9, NB),
+                       "parallelism": "frames sharded by batch, %d rank(s), no data-path collective" % world},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "stage_ms": stage_ms,
+            "fer": {"frames": int(cnt[0]), "ldpc_fer": cnt[2] / max(1, cnt[0]), "bch_fer": cnt[3] / max(1, cnt[0]),
+                    "mean_iterations": cnt[1] / max(1, cnt[0]), "payload_ok": payload_ok},
+        }
+        print(json.dumps(out))
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

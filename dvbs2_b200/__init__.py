@@ -5,7 +5,7 @@ interface.  Nothing in this package imports oracle/.
 """
 from . import capi  # noqa: F401
 from .modules import (Decoder_BCH_DVBS2_cuda, Decoder_chain_DVBS2_cuda, Decoder_LDPC_DVBS2_cuda, Handle,  # noqa: F401
-                      Interleaver_DVBS2_cuda, Modem_DVBS2_cuda)
+                      Interleaver_DVBS2_cuda, Modem_DVBS2_cuda, Transmitter_DVBS2_cuda)
 
 __all__ = ["capi", "Handle", "Modem_DVBS2_cuda", "Interleaver_DVBS2_cuda", "Decoder_LDPC_DVBS2_cuda",
-           "Decoder_BCH_DVBS2_cuda", "Decoder_chain_DVBS2_cuda"]
+           "Decoder_BCH_DVBS2_cuda", "Decoder_chain_DVBS2_cuda", "Transmitter_DVBS2_cuda"]

@@ -21,7 +21,9 @@ SYMBOLS = [
     "dvbs2_cuda_demodulate", "dvbs2_cuda_deinterleave", "dvbs2_cuda_ldpc_decode_siho", "dvbs2_cuda_bch_decode_hiho",
     "dvbs2_cuda_quantize", "dvbs2_cuda_chain", "dvbs2_cuda_host_register", "dvbs2_cuda_host_unregister",
     "dvbs2_cuda_stream", "dvbs2_cuda_sync", "dvbs2_cuda_demodulate_dev", "dvbs2_cuda_ldpc_decode_siho_dev",
-    "dvbs2_cuda_bch_decode_hiho_dev", "dvbs2_cuda_chain_dev",
+    "dvbs2_cuda_bch_decode_hiho_dev", "dvbs2_cuda_chain_dev", "dvbs2_cuda_set_profiling", "dvbs2_cuda_get_timers",
+    "dvbs2_cuda_tx_set_payload", "dvbs2_cuda_tx_random_payload", "dvbs2_cuda_tx_modulate_awgn_dev", "dvbs2_cuda_tx_get_bits",
+    "dvbs2_cuda_monitor_check", "dvbs2_cuda_monitor_get",
 ]
 
 
@@ -39,6 +41,15 @@ class Info(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("frames", "ldpc_iterations", "ldpc_failures", "bch_nonzero", "bch_failures",
                                           "kernel_launches")]
+
+
+class Timers(C.Structure):
+    _fields_ = ([(n + "_ms", C.c_double) for n in ("demap", "ldpc", "bch", "unpack", "pack")] +
+                [(n + "_calls", C.c_uint64) for n in ("demap", "ldpc", "bch", "unpack", "pack")])
+
+
+class Monitor(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_frames", "n_bit_errors", "n_frame_errors")]
 
 
 class Dvbs2CudaError(RuntimeError):
@@ -67,6 +78,8 @@ def load():
     L.dvbs2_cuda_get_info.argtypes = [vp, C.POINTER(Info)]
     L.dvbs2_cuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.dvbs2_cuda_reset_stats.argtypes = [vp]
+    L.dvbs2_cuda_set_profiling.argtypes = [vp, ip]
+    L.dvbs2_cuda_get_timers.argtypes = [vp, C.POINTER(Timers)]
     L.dvbs2_cuda_strerror.argtypes = [ip]
     L.dvbs2_cuda_strerror.restype = C.c_char_p
     L.dvbs2_cuda_last_error.argtypes = [vp]
@@ -87,6 +100,12 @@ def load():
     L.dvbs2_cuda_ldpc_decode_siho_dev.argtypes = [vp, vp, vp, vp, vp, ip]
     L.dvbs2_cuda_bch_decode_hiho_dev.argtypes = [vp, vp, vp, vp, ip]
     L.dvbs2_cuda_chain_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, ip]
+    L.dvbs2_cuda_tx_set_payload.argtypes = [vp, vp, ip]
+    L.dvbs2_cuda_tx_random_payload.argtypes = [vp, C.c_uint64, ip]
+    L.dvbs2_cuda_tx_modulate_awgn_dev.argtypes = [vp, C.c_float, C.c_uint64, vp, vp, ip]
+    L.dvbs2_cuda_tx_get_bits.argtypes = [vp, ip, vp, ip]
+    L.dvbs2_cuda_monitor_check.argtypes = [vp, ip]
+    L.dvbs2_cuda_monitor_get.argtypes = [vp, C.POINTER(Monitor)]
     _lib = L
     return L
 

@@ -27,6 +27,26 @@ struct DevBuf
     void* p = nullptr;
     size_t bytes = 0;
 };
+
+// per-stage device timers (dvbs2_cuda_set_profiling): an event is recorded on the launching stream at every stage
+// boundary; consecutive marks of one stream delimit the stage named by the first of the two
+enum ProfStage
+{
+    P_END = -1,
+    P_DEMAP = 0,
+    P_LDPC,
+    P_BCH,
+    P_UNPACK,
+    P_PACK,
+    P_COUNT
+};
+struct ProfMark
+{
+    cudaEvent_t ev;
+    cudaStream_t s;
+    int stage;
+};
+constexpr size_t PROF_MAX_MARKS = 1 << 15;
 } // namespace
 
 struct dvbs2_cuda_handle
@@ -50,8 +70,17 @@ struct dvbs2_cuda_handle
     DevBuf var, cn, hd, out_hd, rem, nz, cwd_ldpc, cwd_bch, nit, stats;
     // staging for the host-buffer entry points (grown on demand, never beyond max_frames)
     DevBuf in_a, in_b, out_a, sigma;
+    // transmitter / monitor (allocated on first use)
+    DevBuf tx_src, tx_cw, tx_scr, tx_gmask, mon;
+    bool tx_encoded = false;
     uint64_t launches = 0;
     std::string last_error;
+    // profiling
+    bool profiling = false;
+    std::vector<ProfMark> marks;
+    size_t n_marks = 0;
+    double t_ms[P_COUNT] = {};
+    uint64_t t_calls[P_COUNT] = {};
 };
 
 namespace
@@ -76,6 +105,13 @@ fail_cuda(dvbs2_cuda_handle* h, cudaError_t e, const char* what)
         if (e__ != cudaSuccess) return fail_cuda((h), e__, #call);                                                     \
     } while (0)
 
+#define TRY(expr)                                                                                                      \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        int rc__ = (expr);                                                                                             \
+        if (rc__ != DVBS2_OK) return rc__;                                                                             \
+    } while (0)
+
 int
 ensure(dvbs2_cuda_handle* h, DevBuf& b, size_t bytes)
 {
@@ -87,18 +123,54 @@ ensure(dvbs2_cuda_handle* h, DevBuf& b, size_t bytes)
     return DVBS2_OK;
 }
 
-#define TRY(expr)                                                                                                      \
-    do                                                                                                                 \
-    {                                                                                                                  \
-        int rc__ = (expr);                                                                                             \
-        if (rc__ != DVBS2_OK) return rc__;                                                                             \
-    } while (0)
 
 int
 check_frames(dvbs2_cuda_handle* h, int n_frames)
 {
     if (!h || n_frames < 0) return DVBS2_ERR_INVALID;
     if (n_frames > h->max_frames) return DVBS2_ERR_TOO_MANY;
+    return DVBS2_OK;
+}
+
+int
+prof_collect(dvbs2_cuda_handle* h)
+{
+    if (h->n_marks == 0) return DVBS2_OK;
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < N_PIPE; i++)
+        CU(h, cudaStreamSynchronize(h->pipe[i]));
+    for (size_t i = 0; i < h->n_marks; i++)
+    {
+        const ProfMark& a = h->marks[i];
+        if (a.stage < 0) continue;
+        for (size_t j = i + 1; j < h->n_marks; j++)
+            if (h->marks[j].s == a.s)
+            {
+                float ms = 0.f;
+                CU(h, cudaEventElapsedTime(&ms, a.ev, h->marks[j].ev));
+                h->t_ms[a.stage] += ms;
+                h->t_calls[a.stage] += 1;
+                break;
+            }
+    }
+    h->n_marks = 0;
+    return DVBS2_OK;
+}
+
+int
+prof_mark(dvbs2_cuda_handle* h, cudaStream_t s, int stage)
+{
+    if (!h->profiling) return DVBS2_OK;
+    if (h->n_marks == PROF_MAX_MARKS) TRY(prof_collect(h));
+    if (h->n_marks == h->marks.size())
+    {
+        ProfMark m{};
+        CU(h, cudaEventCreate(&m.ev));
+        h->marks.push_back(m);
+    }
+    ProfMark& m = h->marks[h->n_marks++];
+    m.s = s, m.stage = stage;
+    CU(h, cudaEventRecord(m.ev, s));
     return DVBS2_OK;
 }
 
@@ -153,9 +225,13 @@ run_ldpc(dvbs2_cuda_handle* h, cudaStream_t s, int first_group, const void* d_Y,
 {
     if (n_frames == 0) return DVBS2_OK;
     void* var = (char*)h->var.p + (size_t)first_group * N_LDPC * 32 * h->elt;
+    TRY(prof_mark(h, s, P_PACK));
     CU(h, launch_pack_llr(d_Y, var, h->cfg.precision, n_frames, s));
+    TRY(prof_mark(h, s, P_LDPC));
     CU(h, launch_ldpc_decode(ldpc_args(h, first_group, n_frames, d_cwd, d_nit), h->cfg.precision, s));
+    TRY(prof_mark(h, s, P_UNPACK));
     CU(h, launch_unpack_bits((uint32_t*)h->out_hd.p + (size_t)first_group * N_LDPC, d_VK, N_LDPC, h->mc.N_bch, n_frames, s));
+    TRY(prof_mark(h, s, P_END));
     h->launches += 3;
     return DVBS2_OK;
 }
@@ -166,9 +242,13 @@ run_bch(dvbs2_cuda_handle* h, cudaStream_t s, int first_group, const int32_t* d_
 {
     if (n_frames == 0) return DVBS2_OK;
     uint32_t* words = (uint32_t*)h->out_hd.p + (size_t)first_group * N_LDPC;
+    TRY(prof_mark(h, s, P_PACK));
     CU(h, launch_pack_bits(d_Y, words, N_LDPC, h->mc.N_bch, n_frames, s));
+    TRY(prof_mark(h, s, P_BCH));
     CU(h, launch_bch_decode(bch_args(h, first_group, n_frames, d_cwd), h->bch, s));
+    TRY(prof_mark(h, s, P_UNPACK));
     CU(h, launch_unpack_bits(words, d_VK, N_LDPC, h->mc.K_bch, n_frames, s));
+    TRY(prof_mark(h, s, P_END));
     h->launches += 4;
     return DVBS2_OK;
 }
@@ -179,12 +259,60 @@ run_chain(dvbs2_cuda_handle* h, cudaStream_t s, int first_group, const float* d_
 {
     if (n_frames == 0) return DVBS2_OK;
     void* var = (char*)h->var.p + (size_t)first_group * N_LDPC * 32 * h->elt;
+    TRY(prof_mark(h, s, P_DEMAP));
     CU(h, launch_demap_to_var(demap_args(h, d_sigma, d_sym, n_frames), var, h->cfg.precision, s));
+    TRY(prof_mark(h, s, P_LDPC));
     CU(h, launch_ldpc_decode(ldpc_args(h, first_group, n_frames, d_cwd_ldpc, d_nit), h->cfg.precision, s));
+    TRY(prof_mark(h, s, P_BCH));
     CU(h, launch_bch_decode(bch_args(h, first_group, n_frames, d_cwd_bch), h->bch, s));
+    TRY(prof_mark(h, s, P_UNPACK));
     CU(h, launch_unpack_bits((uint32_t*)h->out_hd.p + (size_t)first_group * N_LDPC, d_VK, N_LDPC, h->mc.K_bch, n_frames, s));
+    TRY(prof_mark(h, s, P_END));
     h->launches += 5;
     return DVBS2_OK;
+}
+
+// transmitter state: tables + payload/codeword words for max_frames
+int
+tx_init(dvbs2_cuda_handle* h)
+{
+    if (h->tx_src.p) return DVBS2_OK;
+    std::vector<uint32_t> scr, gm(192, 0u);
+    try
+    {
+        const std::vector<uint8_t> g = build_bch_generator(build_bch_tables());
+        if ((int)g.size() - 1 != h->mc.N_bch - h->mc.K_bch) return DVBS2_ERR_INVALID;
+        for (size_t k = 0; k + 1 < g.size(); k++)
+            gm[k] = g[k] ? 0xffffffffu : 0u;
+        for (uint8_t b : build_bb_scrambler(h->mc.K_bch))
+            scr.push_back(b ? 0xffffffffu : 0u);
+    }
+    catch (const std::exception& e)
+    {
+        h->last_error = e.what();
+        return DVBS2_ERR_INVALID;
+    }
+    const size_t G = (size_t)h->max_groups;
+    TRY(ensure(h, h->tx_scr, scr.size() * 4));
+    TRY(ensure(h, h->tx_gmask, gm.size() * 4));
+    TRY(ensure(h, h->mon, 3 * sizeof(unsigned long long)));
+    TRY(ensure(h, h->tx_cw, G * N_LDPC * 4));
+    CU(h, cudaMemcpy(h->tx_scr.p, scr.data(), scr.size() * 4, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->tx_gmask.p, gm.data(), gm.size() * 4, cudaMemcpyHostToDevice));
+    CU(h, cudaMemset(h->mon.p, 0, h->mon.bytes));
+    TRY(ensure(h, h->tx_src, G * h->mc.K_bch * 4)); // last: its presence marks the transmitter as initialised
+    return DVBS2_OK;
+}
+
+TxLaunch
+tx_args(dvbs2_cuda_handle* h, int n_frames)
+{
+    TxLaunch t{};
+    t.src = (uint32_t*)h->tx_src.p, t.cw = (uint32_t*)h->tx_cw.p;
+    t.scr = (const uint32_t*)h->tx_scr.p, t.gmask = (const uint32_t*)h->tx_gmask.p, t.idx = h->d_idx;
+    t.K_bch = h->mc.K_bch, t.N_bch = h->mc.N_bch, t.d_info = h->lt.d_info, t.d_pad = h->lt.d_pad;
+    t.n_frames = n_frames, t.n_groups = (n_frames + 31) / 32;
+    return t;
 }
 
 // chunking of a host batch over the pipeline streams: chunks are whole groups so their device regions are disjoint
@@ -247,7 +375,8 @@ extern "C"
         if (!h) return DVBS2_OK;
         cudaSetDevice(h->cfg.device);
         for (DevBuf* b : { &h->var, &h->cn, &h->hd, &h->out_hd, &h->rem, &h->nz, &h->cwd_ldpc, &h->cwd_bch, &h->nit,
-                           &h->stats, &h->in_a, &h->in_b, &h->out_a, &h->sigma })
+                           &h->stats, &h->in_a, &h->in_b, &h->out_a, &h->sigma, &h->tx_src, &h->tx_cw, &h->tx_scr,
+                           &h->tx_gmask, &h->mon })
             if (b->p) cudaFree(b->p);
         for (void* p : { (void*)h->d_idx, (void*)h->d_alpha_to, (void*)h->d_index_of, (void*)h->d_cstl })
             if (p) cudaFree(p);
@@ -257,6 +386,8 @@ extern "C"
             if (h->pipe_done[i]) cudaEventDestroy(h->pipe_done[i]);
         }
         if (h->stream) cudaStreamDestroy(h->stream);
+        for (auto& m : h->marks)
+            cudaEventDestroy(m.ev);
         delete h;
         return DVBS2_OK;
     }
@@ -393,6 +524,31 @@ extern "C"
         TRY(dvbs2_cuda_sync(h));
         CU(h, cudaMemset(h->stats.p, 0, h->stats.bytes));
         h->launches = 0;
+        if (h->mon.p) CU(h, cudaMemset(h->mon.p, 0, h->mon.bytes));
+        TRY(prof_collect(h));
+        for (int i = 0; i < P_COUNT; i++)
+            h->t_ms[i] = 0., h->t_calls[i] = 0;
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_set_profiling(dvbs2_cuda_handle* h, int enable)
+    {
+        if (!h) return DVBS2_ERR_INVALID;
+        CU(h, cudaSetDevice(h->cfg.device));
+        if (!enable) TRY(prof_collect(h));
+        h->profiling = enable != 0;
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_get_timers(dvbs2_cuda_handle* h, dvbs2_cuda_timers* t)
+    {
+        if (!h || !t) return DVBS2_ERR_INVALID;
+        CU(h, cudaSetDevice(h->cfg.device));
+        TRY(prof_collect(h));
+        t->demap_ms = h->t_ms[P_DEMAP], t->ldpc_ms = h->t_ms[P_LDPC], t->bch_ms = h->t_ms[P_BCH];
+        t->unpack_ms = h->t_ms[P_UNPACK], t->pack_ms = h->t_ms[P_PACK];
+        t->demap_calls = h->t_calls[P_DEMAP], t->ldpc_calls = h->t_calls[P_LDPC], t->bch_calls = h->t_calls[P_BCH];
+        t->unpack_calls = h->t_calls[P_UNPACK], t->pack_calls = h->t_calls[P_PACK];
         return DVBS2_OK;
     }
 
@@ -598,6 +754,105 @@ extern "C"
         }
         for (int i = 0; i < N_PIPE; i++)
             CU(h, cudaStreamSynchronize(h->pipe[i]));
+        return DVBS2_OK;
+    }
+
+    // ------------------------------------------------------------------------------- transmitter / channel / monitor
+    int dvbs2_cuda_tx_set_payload(dvbs2_cuda_handle* h, const int32_t* U, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!U) return DVBS2_ERR_INVALID;
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        TRY(tx_init(h));
+        const size_t bytes = (size_t)n_frames * h->mc.K_bch * sizeof(int32_t);
+        TRY(ensure(h, h->in_a, bytes));
+        cudaStream_t s = h->stream;
+        CU(h, cudaMemcpyAsync(h->in_a.p, U, bytes, cudaMemcpyHostToDevice, s));
+        CU(h, launch_pack_bits((const int32_t*)h->in_a.p, (uint32_t*)h->tx_src.p, h->mc.K_bch, h->mc.K_bch, n_frames, s));
+        h->launches += 1;
+        h->tx_encoded = false;
+        CU(h, cudaStreamSynchronize(s));
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_tx_random_payload(dvbs2_cuda_handle* h, uint64_t seed, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        TRY(tx_init(h));
+        CU(h, launch_tx_random_payload((uint32_t*)h->tx_src.p, h->mc.K_bch, (n_frames + 31) / 32, seed, h->stream));
+        h->launches += 1;
+        h->tx_encoded = false;
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_tx_modulate_awgn_dev(dvbs2_cuda_handle* h, float sigma, uint64_t seed, float* d_CP, float* d_Y_N1,
+                                        int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!d_CP || !d_Y_N1 || !(sigma >= 0.f) || !h->tx_src.p) return DVBS2_ERR_INVALID;
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        const TxLaunch t = tx_args(h, n_frames);
+        if (!h->tx_encoded)
+        {
+            CU(h, launch_tx_encode(t, h->stream));
+            h->launches += 2;
+            h->tx_encoded = true;
+        }
+        CU(h, launch_tx_modulate_awgn(t, h->d_cstl, d_Y_N1, d_CP, h->mc.bps, h->mc.n_sym, h->mc.itl_cols, h->mc.itl_rev,
+                                      sigma, seed, h->stream));
+        h->launches += 1;
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_tx_get_bits(dvbs2_cuda_handle* h, int stage, int32_t* out, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!out || stage < 0 || stage > 3 || !h->tx_src.p) return DVBS2_ERR_INVALID;
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        if (stage > 0 && !h->tx_encoded)
+        {
+            CU(h, launch_tx_encode(tx_args(h, n_frames), h->stream));
+            h->launches += 2;
+            h->tx_encoded = true;
+        }
+        const int len = stage <= 1 ? h->mc.K_bch : stage == 2 ? h->mc.N_bch : N_LDPC;
+        const uint32_t* words = stage == 0 ? (const uint32_t*)h->tx_src.p : (const uint32_t*)h->tx_cw.p;
+        const int stride = stage == 0 ? h->mc.K_bch : N_LDPC;
+        const size_t bytes = (size_t)n_frames * len * sizeof(int32_t);
+        TRY(ensure(h, h->out_a, bytes));
+        CU(h, launch_unpack_bits(words, (int32_t*)h->out_a.p, stride, len, n_frames, h->stream));
+        h->launches += 1;
+        CU(h, cudaMemcpyAsync(out, h->out_a.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_monitor_check(dvbs2_cuda_handle* h, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!h->tx_src.p) return DVBS2_ERR_INVALID;
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        CU(h, launch_monitor((const uint32_t*)h->out_hd.p, N_LDPC, tx_args(h, n_frames), (unsigned long long*)h->mon.p,
+                             h->stream));
+        h->launches += 1;
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_monitor_get(dvbs2_cuda_handle* h, dvbs2_cuda_monitor* m)
+    {
+        if (!h || !m) return DVBS2_ERR_INVALID;
+        m->n_frames = m->n_bit_errors = m->n_frame_errors = 0;
+        if (!h->mon.p) return DVBS2_OK;
+        TRY(dvbs2_cuda_sync(h));
+        unsigned long long v[3];
+        CU(h, cudaMemcpy(v, h->mon.p, sizeof(v), cudaMemcpyDeviceToHost));
+        m->n_frames = v[0], m->n_bit_errors = v[1], m->n_frame_errors = v[2];
         return DVBS2_OK;
     }
 }

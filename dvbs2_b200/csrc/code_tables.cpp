@@ -130,6 +130,40 @@ build_bch_tables()
     return t;
 }
 
+std::vector<uint8_t>
+build_bch_generator(const BchTables& t)
+{
+    std::vector<uint8_t> g{ 1 };
+    for (int p = 0; p < BCH_NPOLY; p++)
+    {
+        const unsigned mp = (unsigned)t.minpoly[p] | (1u << GF_M);
+        std::vector<uint8_t> nxt(g.size() + GF_M, 0);
+        for (size_t i = 0; i < g.size(); i++)
+            if (g[i])
+                for (int k = 0; k <= GF_M; k++)
+                    if ((mp >> k) & 1u) nxt[i + k] ^= 1;
+        g.swap(nxt);
+    }
+    if (g.size() != (size_t)BCH_NPOLY * GF_M + 1 || !g.front() || !g.back()) throw std::runtime_error("bad BCH generator");
+    return g;
+}
+
+std::vector<uint8_t>
+build_bb_scrambler(int K)
+{
+    int lfsr[15] = { 1, 0, 0, 1, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0 };
+    std::vector<uint8_t> seq(K);
+    for (int i = 0; i < K; i++)
+    {
+        const int fb = lfsr[14] ^ lfsr[13];
+        for (int k = 14; k > 0; k--)
+            lfsr[k] = lfsr[k - 1];
+        lfsr[0] = fb;
+        seq[i] = (uint8_t)fb;
+    }
+    return seq;
+}
+
 std::vector<float>
 build_constellation(int bps)
 {

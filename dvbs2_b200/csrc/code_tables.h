@@ -65,6 +65,11 @@ struct BchTables
     uint16_t synd_mat[2 * BCH_T + 1][GF_M];
 };
 BchTables build_bch_tables();
+// g(x) = product of the 12 minimal polynomials, coefficient of x^k at [k], degree 168 (169 entries of 0/1)
+std::vector<uint8_t> build_bch_generator(const BchTables& t);
+// BB scrambler sequence for K bits: 15-stage LFSR 1 + x^14 + x^15, initial state 100101010000000
+// (src/common/Module/Scrambler/Scrambler_BB/Scrambler_BB.hxx:51-72)
+std::vector<uint8_t> build_bb_scrambler(int K);
 
 // constellation normalised to unit mean energy, index j carries bit b at (j >> b) & 1
 std::vector<float> build_constellation(int bps); // 2 * 2^bps floats (re, im)

@@ -85,4 +85,22 @@ struct BchLaunch
     int N, K;         // shortened BCH length and payload
 };
 cudaError_t launch_bch_decode(const BchLaunch& a, const BchDevTables& t, cudaStream_t s);
+
+// on-device transmitter / channel / monitor (tx_kernel.cu); all buffers bit-sliced per group of 32 frames
+struct TxLaunch
+{
+    uint32_t* src;         // [groups][K_bch]  payload words
+    uint32_t* cw;          // [groups][16200]  codeword words: scrambled payload | BCH parity | LDPC parity
+    const uint32_t* scr;   // [K_bch] BB scrambler sequence, 0 or 0xffffffff per bit
+    const uint32_t* gmask; // [192] BCH generator coefficients g_0..g_167 (then zeros), 0 or 0xffffffff
+    const uint16_t* idx;   // [M][d_pad] LDPC information indices per check
+    int K_bch, N_bch, d_info, d_pad;
+    int n_frames, n_groups;
+};
+cudaError_t launch_tx_random_payload(uint32_t* src, int K, int n_groups, uint64_t seed, cudaStream_t s);
+cudaError_t launch_tx_encode(const TxLaunch& a, cudaStream_t s); // scramble + BCH + LDPC (2 kernels)
+cudaError_t launch_tx_modulate_awgn(const TxLaunch& a, const float* cstl, float* sym, float* cp, int bps, int n_sym,
+                                    int itl_cols, int itl_rev, float sigma, uint64_t seed, cudaStream_t s);
+// mon[0] += frames, mon[1] += bit errors, mon[2] += frame errors of descramble(dec) vs the payload
+cudaError_t launch_monitor(const uint32_t* dec, int dec_stride, const TxLaunch& a, unsigned long long* mon, cudaStream_t s);
 } // namespace dvbs2

@@ -95,6 +95,15 @@ class Handle:
     def reset_stats(self):
         self.check(self.lib.dvbs2_cuda_reset_stats(self._h))
 
+    def set_profiling(self, enable=True):
+        """Per-stage device timers (CUDA events on the launching stream around every kernel of the chain)."""
+        self.check(self.lib.dvbs2_cuda_set_profiling(self._h, int(bool(enable))))
+
+    def timers(self):
+        t = capi.Timers()
+        self.check(self.lib.dvbs2_cuda_get_timers(self._h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in capi.Timers._fields_}
+
     def host_register(self, arr):
         self.check(self.lib.dvbs2_cuda_host_register(self._h, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
 
@@ -221,3 +230,47 @@ class Decoder_chain_DVBS2_cuda(_Module):
             None if CWD_bch is None else _dev_ptr(CWD_bch, "int8", F, "CWD_bch"),
             _dev_ptr(V_K, "int32", F * self.K, "V_K"),
             None if n_iter is None else _dev_ptr(n_iter, "int32", F, "n_iter"), F))
+
+
+class Transmitter_DVBS2_cuda(_Module):
+    """On-device TX chain + AWGN channel + BFER monitor around the decode path (Monte-Carlo / benchmark harness):
+    Source -> Scrambler_BB.scramble -> Encoder_BCH_DVBS2 -> Encoder_LDPC_DVBS2 -> interleave -> modulate -> add_noise
+    (mains/TX_RX_BB/main.cpp:75-84) and, behind the chain, Scrambler_BB.descramble -> Monitor_BFER.check_errors (:92-94)."""
+
+    STAGES = {"payload": 0, "scrambled": 1, "bch": 2, "ldpc": 3}
+
+    def __init__(self, handle, n_frames=1):
+        super().__init__(handle, n_frames)
+        self.K = handle.info["K_bch"]
+        self.N_fil = 2 * handle.info["n_sym"]
+
+    def set_payload(self, U):
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_tx_set_payload(h._h, _np_ptr(U, np.int32, F * self.K, "U"), F))
+
+    def random_payload(self, seed):
+        h = self.h
+        h.check(h.lib.dvbs2_cuda_tx_random_payload(h._h, int(seed), self.n_frames))
+
+    def modulate_awgn_dev(self, sigma, seed, CP, Y_N1):
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_tx_modulate_awgn_dev(h._h, float(sigma), int(seed), _dev_ptr(CP, "float32", F, "CP"),
+                                                      _dev_ptr(Y_N1, "float32", F * self.N_fil, "Y_N1"), F))
+
+    def get_bits(self, stage):
+        F, h = self.n_frames, self.h
+        n = {0: self.K, 1: self.K, 2: h.info["N_bch"], 3: N_LDPC}[self.STAGES[stage]]
+        out = np.zeros((F, n), np.int32)
+        h.check(h.lib.dvbs2_cuda_tx_get_bits(h._h, self.STAGES[stage], out.ctypes.data_as(C.c_void_p), F))
+        return out
+
+    def check_errors(self):
+        """Queue the comparison of the last chain output on this handle with the payload (asynchronous)."""
+        h = self.h
+        h.check(h.lib.dvbs2_cuda_monitor_check(h._h, self.n_frames))
+
+    def monitor(self):
+        m = capi.Monitor()
+        h = self.h
+        h.check(h.lib.dvbs2_cuda_monitor_get(h._h, C.byref(m)))
+        return {"n_frames": int(m.n_frames), "n_be": int(m.n_bit_errors), "n_fe": int(m.n_frame_errors)}

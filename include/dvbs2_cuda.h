@@ -95,6 +95,15 @@ extern "C"
         uint64_t kernel_launches; /* kernels launched by this handle                                        */
     } dvbs2_cuda_stats;
 
+    /* device time per stage, measured with CUDA events recorded on the launching stream around each kernel of the
+     * chain while profiling is enabled (the reference's per-task timers: Task::set_stats / register_timer,
+     * S/src/Runtime/Task/Task.cpp:348-365).  *_ms are sums over the *_calls launches since the last reset_stats. */
+    typedef struct
+    {
+        double demap_ms, ldpc_ms, bch_ms, unpack_ms, pack_ms;
+        uint64_t demap_calls, ldpc_calls, bch_calls, unpack_calls, pack_calls;
+    } dvbs2_cuda_timers;
+
     typedef struct dvbs2_cuda_handle dvbs2_cuda_handle;
 
     void dvbs2_cuda_default_cfg(dvbs2_cuda_cfg* cfg); /* QPSK-S_8/9, 10 it, norm 1.0, f32, early stop, 1024 frames */
@@ -103,6 +112,8 @@ extern "C"
     int dvbs2_cuda_get_info(const dvbs2_cuda_handle* h, dvbs2_cuda_info* info);
     int dvbs2_cuda_get_stats(dvbs2_cuda_handle* h, dvbs2_cuda_stats* stats); /* synchronises the stream */
     int dvbs2_cuda_reset_stats(dvbs2_cuda_handle* h);
+    int dvbs2_cuda_set_profiling(dvbs2_cuda_handle* h, int enable);            /* default off */
+    int dvbs2_cuda_get_timers(dvbs2_cuda_handle* h, dvbs2_cuda_timers* timers); /* synchronises the stream */
     const char* dvbs2_cuda_strerror(int status);
     const char* dvbs2_cuda_last_error(const dvbs2_cuda_handle* h); /* text of the last CUDA failure */
     int dvbs2_cuda_device_count(void);
@@ -143,6 +154,32 @@ extern "C"
                                        int n_frames);
     int dvbs2_cuda_chain_dev(dvbs2_cuda_handle* h, const float* d_CP, const float* d_Y_N1, int8_t* d_CWD_ldpc,
                              int8_t* d_CWD_bch, int32_t* d_V_K, int32_t* d_n_iter, int n_frames);
+
+    /* ---- on-device transmitter, AWGN channel and BER/FER monitor ------------------------------------------------
+     * Monte-Carlo / benchmark harness around the decode path: what D/mains/TX_RX_BB/main.cpp:75-84
+     * chains in front of the receiver (Source -> Scrambler_BB::scramble -> Encoder_BCH_DVBS2 -> Encoder_LDPC_DVBS2 ->
+     * Interleaver::interleave -> Modem::modulate -> Channel_AWGN_LLR::add_noise) and what it chains behind it
+     * (Scrambler_BB::descramble -> Monitor_BFER::check_errors, main.cpp:92-94), so frames can be produced and scored in
+     * HBM.  The payload of the last tx call stays in the handle for the monitor. */
+    typedef struct
+    {
+        uint64_t n_frames, n_bit_errors, n_frame_errors; /* Monitor_BFER counters (FRA, BE, FE) */
+    } dvbs2_cuda_monitor;
+
+    /* payload from the host: U[F][K_bch] int32 0/1 */
+    int dvbs2_cuda_tx_set_payload(dvbs2_cuda_handle* h, const int32_t* U, int n_frames);
+    /* payload generated on the device (counter-based hash of seed, frame, bit) */
+    int dvbs2_cuda_tx_random_payload(dvbs2_cuda_handle* h, uint64_t seed, int n_frames);
+    /* scramble + BCH + LDPC encode the payload, interleave, map, add AWGN of std-dev sigma per dimension (sigma = 0: no
+     * noise): d_CP[F] <- sigma, d_Y_N1[F][2*n_sym] <- received symbols.  Device pointers, asynchronous. */
+    int dvbs2_cuda_tx_modulate_awgn_dev(dvbs2_cuda_handle* h, float sigma, uint64_t seed, float* d_CP, float* d_Y_N1,
+                                        int n_frames);
+    /* bits of the last tx call, to the host: stage 0 payload [F][K_bch], 1 scrambled [F][K_bch], 2 BCH codeword
+     * [F][N_bch], 3 LDPC codeword [F][16200] (natural order) */
+    int dvbs2_cuda_tx_get_bits(dvbs2_cuda_handle* h, int stage, int32_t* out, int n_frames);
+    /* descramble the BCH output of the last chain call on this handle and compare with the payload (asynchronous) */
+    int dvbs2_cuda_monitor_check(dvbs2_cuda_handle* h, int n_frames);
+    int dvbs2_cuda_monitor_get(dvbs2_cuda_handle* h, dvbs2_cuda_monitor* m); /* synchronises; reset_stats clears it */
 
 #ifdef __cplusplus
 }
