@@ -54,7 +54,8 @@ struct dvbs2_cuda_handle
     dvbs2_cuda_cfg cfg{};
     ModcodParams mc{};
     LdpcTables lt;
-    int max_frames = 0, max_groups = 0;
+    int max_frames = 0, max_groups = 0; // max_groups counts 32-frame subgroups
+    int nf = 1, n_sms = 148;             // frames per lane of the LDPC kernel (group = 32 * nf frames)
     int k8 = 0;
     size_t elt = 4; // sizeof(R)
     cudaStream_t stream = nullptr;
@@ -62,6 +63,9 @@ struct dvbs2_cuda_handle
     cudaEvent_t pipe_done[N_PIPE] = {};
     // code tables
     uint16_t* d_idx = nullptr;
+    uint32_t* d_idx32 = nullptr;
+    uint32_t* d_last = nullptr;
+    int* d_queue = nullptr;
     uint16_t* d_alpha_to = nullptr;
     int16_t* d_index_of = nullptr;
     float* d_cstl = nullptr;
@@ -174,33 +178,40 @@ prof_mark(dvbs2_cuda_handle* h, cudaStream_t s, int stage)
     return DVBS2_OK;
 }
 
+// `first_frame` is a multiple of the group size 32 * nf; per-frame offsets follow from the layouts in kernels.h
 LdpcLaunch
-ldpc_args(dvbs2_cuda_handle* h, int first_group, int n_frames, int8_t* cwd, int32_t* n_iter)
+ldpc_args(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frames, int8_t* cwd, int32_t* n_iter)
 {
     LdpcLaunch a{};
-    a.var = (char*)h->var.p + (size_t)first_group * N_LDPC * 32 * h->elt;
-    a.cn = (uint4*)h->cn.p + (size_t)first_group * h->mc.M * 32;
-    a.hd = (uint32_t*)h->hd.p + (size_t)first_group * N_LDPC;
-    a.out_hd = (uint32_t*)h->out_hd.p + (size_t)first_group * N_LDPC;
-    a.idx = h->d_idx;
+    a.var = (char*)h->var.p + (size_t)first_frame * N_LDPC * h->elt;
+    a.cn = (uint4*)h->cn.p + (size_t)first_frame * h->mc.M;
+    a.hd = (uint32_t*)h->hd.p + (size_t)(first_frame / 32) * N_LDPC;
+    a.out_hd = (uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC;
+    a.idx32 = h->d_idx32, a.last = h->d_last;
+    int slot = 0; // launches of one stream are ordered, so one queue head per stream is enough
+    for (int i = 0; i < N_PIPE; i++)
+        if (s == h->pipe[i]) slot = 1 + i;
+    a.queue = h->d_queue + slot;
     a.cwd = cwd;
     a.n_iter = n_iter;
     a.stats = (unsigned long long*)h->stats.p;
     a.n_frames = n_frames;
-    a.n_groups = (n_frames + 31) / 32;
+    a.n_groups = (n_frames + 32 * h->nf - 1) / (32 * h->nf);
     a.K = h->mc.N_bch, a.M = h->mc.M, a.d_info = h->mc.d_info;
     a.n_ite = h->cfg.n_ite, a.norm = h->cfg.norm, a.k8 = h->k8, a.early_stop = h->cfg.early_stop;
+    a.n_sms = h->n_sms;
     return a;
 }
 
 BchLaunch
-bch_args(dvbs2_cuda_handle* h, int first_group, int n_frames, int8_t* cwd)
+bch_args(dvbs2_cuda_handle* h, int first_frame, int n_frames, int8_t* cwd)
 {
+    const int sg = first_frame / 32;
     BchLaunch b{};
-    b.words = (uint32_t*)h->out_hd.p + (size_t)first_group * N_LDPC;
+    b.words = (uint32_t*)h->out_hd.p + (size_t)sg * N_LDPC;
     b.stride = N_LDPC;
-    b.rem = (uint32_t*)h->rem.p + (size_t)first_group * BCH_NPOLY * GF_M;
-    b.nz = (uint32_t*)h->nz.p + first_group;
+    b.rem = (uint32_t*)h->rem.p + (size_t)sg * BCH_NPOLY * GF_M;
+    b.nz = (uint32_t*)h->nz.p + sg;
     b.cwd = cwd;
     b.stats = (unsigned long long*)h->stats.p;
     b.n_frames = n_frames, b.n_groups = (n_frames + 31) / 32;
@@ -218,34 +229,34 @@ demap_args(dvbs2_cuda_handle* h, const float* d_sigma, const float* d_sym, int n
     return d;
 }
 
-// device-side pieces, all asynchronous on `s`; frames occupy groups [first_group, ...)
+// device-side pieces, all asynchronous on `s`; frames occupy device slots [first_frame, ...), first_frame a multiple of the group size
 int
-run_ldpc(dvbs2_cuda_handle* h, cudaStream_t s, int first_group, const void* d_Y, int8_t* d_cwd, int32_t* d_VK,
+run_ldpc(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const void* d_Y, int8_t* d_cwd, int32_t* d_VK,
          int32_t* d_nit, int n_frames)
 {
     if (n_frames == 0) return DVBS2_OK;
-    void* var = (char*)h->var.p + (size_t)first_group * N_LDPC * 32 * h->elt;
+    void* var = (char*)h->var.p + (size_t)first_frame * N_LDPC * h->elt;
     TRY(prof_mark(h, s, P_PACK));
     CU(h, launch_pack_llr(d_Y, var, h->cfg.precision, n_frames, s));
     TRY(prof_mark(h, s, P_LDPC));
-    CU(h, launch_ldpc_decode(ldpc_args(h, first_group, n_frames, d_cwd, d_nit), h->cfg.precision, s));
+    CU(h, launch_ldpc_decode(ldpc_args(h, s, first_frame, n_frames, d_cwd, d_nit), h->cfg.precision, s));
     TRY(prof_mark(h, s, P_UNPACK));
-    CU(h, launch_unpack_bits((uint32_t*)h->out_hd.p + (size_t)first_group * N_LDPC, d_VK, N_LDPC, h->mc.N_bch, n_frames, s));
+    CU(h, launch_unpack_bits((uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC, d_VK, N_LDPC, h->mc.N_bch, n_frames, s));
     TRY(prof_mark(h, s, P_END));
     h->launches += 3;
     return DVBS2_OK;
 }
 
 int
-run_bch(dvbs2_cuda_handle* h, cudaStream_t s, int first_group, const int32_t* d_Y, int8_t* d_cwd, int32_t* d_VK,
+run_bch(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const int32_t* d_Y, int8_t* d_cwd, int32_t* d_VK,
         int n_frames)
 {
     if (n_frames == 0) return DVBS2_OK;
-    uint32_t* words = (uint32_t*)h->out_hd.p + (size_t)first_group * N_LDPC;
+    uint32_t* words = (uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC;
     TRY(prof_mark(h, s, P_PACK));
     CU(h, launch_pack_bits(d_Y, words, N_LDPC, h->mc.N_bch, n_frames, s));
     TRY(prof_mark(h, s, P_BCH));
-    CU(h, launch_bch_decode(bch_args(h, first_group, n_frames, d_cwd), h->bch, s));
+    CU(h, launch_bch_decode(bch_args(h, first_frame, n_frames, d_cwd), h->bch, s));
     TRY(prof_mark(h, s, P_UNPACK));
     CU(h, launch_unpack_bits(words, d_VK, N_LDPC, h->mc.K_bch, n_frames, s));
     TRY(prof_mark(h, s, P_END));
@@ -254,19 +265,19 @@ run_bch(dvbs2_cuda_handle* h, cudaStream_t s, int first_group, const int32_t* d_
 }
 
 int
-run_chain(dvbs2_cuda_handle* h, cudaStream_t s, int first_group, const float* d_sigma, const float* d_sym,
+run_chain(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const float* d_sigma, const float* d_sym,
           int8_t* d_cwd_ldpc, int8_t* d_cwd_bch, int32_t* d_VK, int32_t* d_nit, int n_frames)
 {
     if (n_frames == 0) return DVBS2_OK;
-    void* var = (char*)h->var.p + (size_t)first_group * N_LDPC * 32 * h->elt;
+    void* var = (char*)h->var.p + (size_t)first_frame * N_LDPC * h->elt;
     TRY(prof_mark(h, s, P_DEMAP));
-    CU(h, launch_demap_to_var(demap_args(h, d_sigma, d_sym, n_frames), var, h->cfg.precision, s));
+    CU(h, launch_demap_to_var(demap_args(h, d_sigma, d_sym, n_frames), var, h->cfg.precision, h->nf, s));
     TRY(prof_mark(h, s, P_LDPC));
-    CU(h, launch_ldpc_decode(ldpc_args(h, first_group, n_frames, d_cwd_ldpc, d_nit), h->cfg.precision, s));
+    CU(h, launch_ldpc_decode(ldpc_args(h, s, first_frame, n_frames, d_cwd_ldpc, d_nit), h->cfg.precision, s));
     TRY(prof_mark(h, s, P_BCH));
-    CU(h, launch_bch_decode(bch_args(h, first_group, n_frames, d_cwd_bch), h->bch, s));
+    CU(h, launch_bch_decode(bch_args(h, first_frame, n_frames, d_cwd_bch), h->bch, s));
     TRY(prof_mark(h, s, P_UNPACK));
-    CU(h, launch_unpack_bits((uint32_t*)h->out_hd.p + (size_t)first_group * N_LDPC, d_VK, N_LDPC, h->mc.K_bch, n_frames, s));
+    CU(h, launch_unpack_bits((uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC, d_VK, N_LDPC, h->mc.K_bch, n_frames, s));
     TRY(prof_mark(h, s, P_END));
     h->launches += 5;
     return DVBS2_OK;
@@ -321,7 +332,7 @@ chunk_frames(const dvbs2_cuda_handle* h, int n_frames)
 {
     int per = (n_frames + N_PIPE * 2 - 1) / (N_PIPE * 2); // ~6 chunks per call
     per = std::max(per, 4096);                             // below this the kernels are launch/latency bound anyway
-    per = (per + 31) / 32 * 32;
+    per = (per + 255) / 256 * 256;                         // whole decoder groups for every precision
     (void)h;
     return per;
 }
@@ -378,7 +389,8 @@ extern "C"
                            &h->stats, &h->in_a, &h->in_b, &h->out_a, &h->sigma, &h->tx_src, &h->tx_cw, &h->tx_scr,
                            &h->tx_gmask, &h->mon })
             if (b->p) cudaFree(b->p);
-        for (void* p : { (void*)h->d_idx, (void*)h->d_alpha_to, (void*)h->d_index_of, (void*)h->d_cstl })
+        for (void* p : { (void*)h->d_idx, (void*)h->d_idx32, (void*)h->d_last, (void*)h->d_queue, (void*)h->d_alpha_to,
+                         (void*)h->d_index_of, (void*)h->d_cstl })
             if (p) cudaFree(p);
         for (int i = 0; i < N_PIPE; i++)
         {
@@ -420,8 +432,9 @@ extern "C"
         h->mc = mc;
         h->k8 = k8;
         h->elt = cfg->precision == DVBS2_PREC_F32 ? 4 : cfg->precision == DVBS2_PREC_I16 ? 2 : 1;
-        h->max_groups = (cfg->max_frames + 31) / 32;
-        h->max_frames = h->max_groups * 32;
+        h->nf = ldpc_frames_per_lane(cfg->precision);
+        h->max_frames = (cfg->max_frames + 32 * h->nf - 1) / (32 * h->nf) * (32 * h->nf);
+        h->max_groups = h->max_frames / 32;
 
         auto bail = [&](int rc) {
             dvbs2_cuda_destroy(h);
@@ -458,6 +471,14 @@ extern "C"
         }
         CUB(cudaMalloc(&h->d_idx, h->lt.idx.size() * sizeof(uint16_t)));
         CUB(cudaMemcpy(h->d_idx, h->lt.idx.data(), h->lt.idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&h->d_idx32, h->lt.idx32.size() * sizeof(uint32_t)));
+        CUB(cudaMemcpy(h->d_idx32, h->lt.idx32.data(), h->lt.idx32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&h->d_last, h->lt.last.size() * sizeof(uint32_t)));
+        CUB(cudaMemcpy(h->d_last, h->lt.last.data(), h->lt.last.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&h->d_queue, 64 * sizeof(int)));
+        CUB(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+        // the decoder prefetches one check ahead: legal only while no two checks that close share an information variable
+        if (h->lt.min_reuse_distance < 4) return bail(DVBS2_ERR_INVALID);
         CUB(cudaMalloc(&h->d_alpha_to, bt.alpha_to.size() * sizeof(uint16_t)));
         CUB(cudaMemcpy(h->d_alpha_to, bt.alpha_to.data(), bt.alpha_to.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
         CUB(cudaMalloc(&h->d_index_of, bt.index_of.size() * sizeof(int16_t)));
@@ -683,7 +704,7 @@ extern "C"
             int8_t* d_cwd = (int8_t*)h->cwd_ldpc.p + f0;
             int32_t* d_nit = (int32_t*)h->nit.p + f0;
             CU(h, cudaMemcpyAsync(d_in, (const char*)Y_N + inf * f0, inf * nf, cudaMemcpyHostToDevice, s));
-            TRY(run_ldpc(h, s, f0 / 32, d_in, d_cwd, d_out, d_nit, nf));
+            TRY(run_ldpc(h, s, f0, d_in, d_cwd, d_out, d_nit, nf));
             CU(h, cudaMemcpyAsync((char*)V_K + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
             if (CWD) CU(h, cudaMemcpyAsync(CWD + f0, d_cwd, nf, cudaMemcpyDeviceToHost, s));
             if (n_iter) CU(h, cudaMemcpyAsync(n_iter + f0, d_nit, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, s));
@@ -712,7 +733,7 @@ extern "C"
             int32_t* d_out = (int32_t*)((char*)h->out_a.p + outf * f0);
             int8_t* d_cwd = (int8_t*)h->cwd_bch.p + f0;
             CU(h, cudaMemcpyAsync(d_in, (const char*)Y_N + inf * f0, inf * nf, cudaMemcpyHostToDevice, s));
-            TRY(run_bch(h, s, f0 / 32, d_in, d_cwd, d_out, nf));
+            TRY(run_bch(h, s, f0, d_in, d_cwd, d_out, nf));
             CU(h, cudaMemcpyAsync((char*)V_K + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
             if (CWD) CU(h, cudaMemcpyAsync(CWD + f0, d_cwd, nf, cudaMemcpyDeviceToHost, s));
         }
@@ -746,7 +767,7 @@ extern "C"
             int32_t* d_nit = (int32_t*)h->nit.p + f0;
             CU(h, cudaMemcpyAsync(d_sig, CP + f0, sizeof(float) * nf, cudaMemcpyHostToDevice, s));
             CU(h, cudaMemcpyAsync(d_sym, (const char*)Y_N1 + inf * f0, inf * nf, cudaMemcpyHostToDevice, s));
-            TRY(run_chain(h, s, f0 / 32, d_sig, d_sym, d_c1, d_c2, d_out, d_nit, nf));
+            TRY(run_chain(h, s, f0, d_sig, d_sym, d_c1, d_c2, d_out, d_nit, nf));
             CU(h, cudaMemcpyAsync((char*)V_K + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
             if (CWD_ldpc) CU(h, cudaMemcpyAsync(CWD_ldpc + f0, d_c1, nf, cudaMemcpyDeviceToHost, s));
             if (CWD_bch) CU(h, cudaMemcpyAsync(CWD_bch + f0, d_c2, nf, cudaMemcpyDeviceToHost, s));

@@ -65,6 +65,29 @@ build_ldpc_tables(int K)
         std::copy(per_check[c].begin(), per_check[c].end(), t.idx.begin() + (size_t)c * t.d_pad);
     // + the dual diagonal: check c also holds parity bits K+c-1 (c>0) and K+c
     t.E = t.M * (t.d_info + 2) - 1;
+
+    t.iw = (t.d_info + 1) / 2;
+    t.idx32.assign((size_t)t.M * t.iw, 0u);
+    t.last.assign(t.M, 0u);
+    std::vector<int> last_check(K, -1), first_check(K, -1), prev_check(K, -1);
+    t.min_reuse_distance = t.M;
+    for (int c = 0; c < t.M; c++)
+        for (int i = 0; i < t.d_info; i++)
+        {
+            const int v = per_check[c][i];
+            t.idx32[(size_t)c * t.iw + i / 2] |= (uint32_t)v << ((i & 1) * 16);
+            if (first_check[v] < 0) first_check[v] = c;
+            if (prev_check[v] >= 0) t.min_reuse_distance = std::min(t.min_reuse_distance, c - prev_check[v]);
+            prev_check[v] = last_check[v] = c;
+        }
+    for (int v = 0; v < K; v++)
+    {
+        if (last_check[v] < 0) throw std::runtime_error("information variable without a check");
+        t.min_reuse_distance = std::min(t.min_reuse_distance, first_check[v] + t.M - last_check[v]);
+    }
+    for (int c = 0; c < t.M; c++)
+        for (int i = 0; i < t.d_info; i++)
+            if (last_check[per_check[c][i]] == c) t.last[c] |= 1u << i;
     return t;
 }
 

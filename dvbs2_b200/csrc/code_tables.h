@@ -51,6 +51,12 @@ struct LdpcTables
 {
     int K, M, E, d_info, d_pad;     // d_pad: row stride of idx (multiple of 8 so rows are uint4-loadable)
     std::vector<uint16_t> idx;      // [M][d_pad] information variables of check c, ascending; padding = 0xFFFF
+    // the same rows packed for the decoder's shared-memory copy: [M][iw] u32, two indices per word (low half first)
+    int iw;
+    std::vector<uint32_t> idx32;
+    // [M] bit i set: check c is the LAST check (natural order) that updates information variable idx[c][i]
+    std::vector<uint32_t> last;
+    int min_reuse_distance;         // smallest gap (in checks, cyclically) between two checks sharing an information variable
 };
 // throws std::runtime_error on malformed tables
 LdpcTables build_ldpc_tables(int K_ldpc);

@@ -99,11 +99,11 @@ demap_frames_kernel(const DemapLaunch a, float* __restrict__ llr, int deinterlea
         o[deinterleave ? natural_pos(k, b, BPS, a.n_sym, a.itl_cols, a.itl_rev) : k * BPS + b] = out[b];
 }
 
-// warp = (group of 32 frames, 16 consecutive symbols); lane = frame.  Symbols are staged through shared memory so the
+// warp = (subgroup of 32 frames, 16 consecutive symbols); lane = frame.  Symbols are staged through shared memory so the
 // global reads are 128-byte rows of one frame and the global writes are 32-lane rows of one variable.
 constexpr int DEMAP_WARPS = 4;
 template<int BPS, typename R>
-__global__ void __launch_bounds__(DEMAP_WARPS * 32) demap_to_var_kernel(const DemapLaunch a, R* __restrict__ var)
+__global__ void __launch_bounds__(DEMAP_WARPS * 32) demap_to_var_kernel(const DemapLaunch a, R* __restrict__ var, int nf)
 {
     __shared__ float cs[2 << BPS];
     __shared__ float tile[DEMAP_WARPS][32][33];
@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(DEMAP_WARPS * 32) demap_to_var_kernel(const De
     const float inv = 1.0f / (2 * sg * sg);
     const float factor = (float)(1 << a.quant_dec);
     const float vmax = (float)((1 << (a.quant_bits - 1)) - 1);
-    R* vg = var + (size_t)g * N_LDPC * 32 + lane;
+    // subgroup g = group g / nf, slot g % nf of the decoder's var[group][v][lane][nf] layout
+    R* vg = var + ((size_t)(g / nf) * N_LDPC * 32 + lane) * nf + g % nf;
 #pragma unroll 4
     for (int s = 0; s < 16; s++)
     {
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(DEMAP_WARPS * 32) demap_to_var_kernel(const De
         for (int b = 0; b < BPS; b++)
         {
             const int v = natural_pos(k, b, BPS, a.n_sym, a.itl_cols, a.itl_rev);
-            vg[(size_t)v * 32] = frame < a.n_frames ? quantize<R>(out[b], factor, vmax) : (R)0;
+            vg[(size_t)v * 32 * nf] = frame < a.n_frames ? quantize<R>(out[b], factor, vmax) : (R)0;
         }
     }
 }
@@ -177,28 +178,28 @@ launch_demap_frames(const DemapLaunch& a, float* llr, int deinterleave, cudaStre
 
 template<int BPS>
 static cudaError_t
-demap_to_var_bps(const DemapLaunch& a, void* var, int precision, cudaStream_t s)
+demap_to_var_bps(const DemapLaunch& a, void* var, int precision, int nf, cudaStream_t s)
 {
-    const int groups = (a.n_frames + 31) / 32;
+    const int groups = (a.n_frames + 32 * nf - 1) / (32 * nf) * nf; // whole decoder groups: pad subgroups get zeros
     const dim3 grid((a.n_sym + 16 * DEMAP_WARPS - 1) / (16 * DEMAP_WARPS), groups);
     switch (precision)
     {
-        case 0: demap_to_var_kernel<BPS, float><<<grid, DEMAP_WARPS * 32, 0, s>>>(a, (float*)var); break;
-        case 1: demap_to_var_kernel<BPS, int16_t><<<grid, DEMAP_WARPS * 32, 0, s>>>(a, (int16_t*)var); break;
-        case 2: demap_to_var_kernel<BPS, int8_t><<<grid, DEMAP_WARPS * 32, 0, s>>>(a, (int8_t*)var); break;
+        case 0: demap_to_var_kernel<BPS, float><<<grid, DEMAP_WARPS * 32, 0, s>>>(a, (float*)var, nf); break;
+        case 1: demap_to_var_kernel<BPS, int16_t><<<grid, DEMAP_WARPS * 32, 0, s>>>(a, (int16_t*)var, nf); break;
+        case 2: demap_to_var_kernel<BPS, int8_t><<<grid, DEMAP_WARPS * 32, 0, s>>>(a, (int8_t*)var, nf); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
 
 cudaError_t
-launch_demap_to_var(const DemapLaunch& a, void* var, int precision, cudaStream_t s)
+launch_demap_to_var(const DemapLaunch& a, void* var, int precision, int nf, cudaStream_t s)
 {
     switch (a.bps)
     {
-        case 2: return demap_to_var_bps<2>(a, var, precision, s);
-        case 3: return demap_to_var_bps<3>(a, var, precision, s);
-        case 4: return demap_to_var_bps<4>(a, var, precision, s);
+        case 2: return demap_to_var_bps<2>(a, var, precision, nf, s);
+        case 3: return demap_to_var_bps<3>(a, var, precision, nf, s);
+        case 4: return demap_to_var_bps<4>(a, var, precision, nf, s);
     }
     return cudaErrorInvalidValue;
 }

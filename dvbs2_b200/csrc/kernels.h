@@ -7,7 +7,7 @@
 
 namespace dvbs2
 {
-constexpr int LDPC_WARPS_PER_BLOCK = 4;
+constexpr int LDPC_WARPS_PER_BLOCK = 8;
 
 enum StatSlot
 {
@@ -19,20 +19,24 @@ enum StatSlot
     STAT_COUNT
 };
 
-// Device-resident layout shared by the kernels ("group" = 32 consecutive frames, lane = frame % 32):
-//   var    [groups][16200][32]  R       variable-node values (LLR + messages), lane-interleaved
-//   cn     [groups][M][32]      uint4   compressed check state {out1, out2, sign bits, eq bits}
-//   hd     [groups][16200]      u32     running hard decisions, bit f = frame f of the group
-//   out_hd [groups][16200]      u32     hard decisions snapshotted when each frame stopped iterating
+// Device-resident layout shared by the kernels.  "subgroup" = 32 consecutive frames (bit f of a bit-sliced word =
+// frame 32*subgroup + f); "group" = NF consecutive subgroups decoded by one warp, NF = ldpc_frames_per_lane(precision):
+//   var    [groups][16200][32][NF]   R      variable-node values (LLR + messages); element (lane l, j) = frame
+//                                            (group*NF + j)*32 + l
+//   cn     [groups][M][NF][32]       uint4  compressed check state {out1, out2, sign bits, eq bits}
+//   hd     [subgroups][16200]        u32    running hard decisions
+//   out_hd [subgroups][16200]        u32    hard decisions snapshotted when each frame stopped iterating
 struct LdpcLaunch
 {
     void* var;
     uint4* cn;
     uint32_t* hd;
     uint32_t* out_hd;
-    const uint16_t* idx; // [M][d_pad]
-    int8_t* cwd;         // [frames] or null
-    int32_t* n_iter;     // [frames] or null
+    const uint32_t* idx32; // [M][(d_info+1)/2] information-variable indices, two per word
+    const uint32_t* last;  // [M] bit i: check c is the last one of the iteration to update its i-th information variable
+    int* queue;            // work queue head (zeroed by the launcher)
+    int8_t* cwd;           // [frames] or null
+    int32_t* n_iter;       // [frames] or null
     unsigned long long* stats;
     int n_frames, n_groups;
     int K, M, d_info;
@@ -40,8 +44,10 @@ struct LdpcLaunch
     float norm;
     int k8; // norm * 8 if that is an integer in 1..8, else 0
     int early_stop;
+    int n_sms;
 };
 
+int ldpc_frames_per_lane(int precision); // NF: 2 (f32, i16), 4 (i8)
 cudaError_t launch_ldpc_decode(const LdpcLaunch& a, int precision, cudaStream_t s);
 cudaError_t launch_pack_llr(const void* in, void* var, int precision, int n_frames, cudaStream_t s);
 cudaError_t launch_unpack_bits(const uint32_t* words, int32_t* out, int stride, int K, int n_frames, cudaStream_t s);
@@ -59,8 +65,8 @@ struct DemapLaunch
 };
 // frame-major float LLRs; deinterleave = 0 gives Modem::demodulate order, 1 gives natural order
 cudaError_t launch_demap_frames(const DemapLaunch& a, float* llr, int deinterleave, cudaStream_t s);
-// straight into the decoder's lane-interleaved var layout (natural order), quantised for integer precisions
-cudaError_t launch_demap_to_var(const DemapLaunch& a, void* var, int precision, cudaStream_t s);
+// straight into the decoder's lane-interleaved var layout (natural order, nf frames per lane), quantised for integers
+cudaError_t launch_demap_to_var(const DemapLaunch& a, void* var, int precision, int nf, cudaStream_t s);
 cudaError_t launch_deinterleave(const float* itl, float* nat, int n_frames, int n_sym, int itl_cols, int itl_rev,
                                 cudaStream_t s);
 cudaError_t launch_quantize(const float* in, void* out, int precision, size_t n, int dec, int bits, cudaStream_t s);

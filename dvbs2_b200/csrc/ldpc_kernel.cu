@@ -5,22 +5,31 @@
 // 100-106 and LDPC_syndrome.hxx:43-69 — checks are visited in natural order c = 0..M-1 (the IRA dual diagonal makes
 // that a strict chain), per-frame syndrome early termination.
 //
-// B200 mapping ("lane = frame"): a warp owns a group of 32 frames and walks the checks in order; lane f holds frame f.
-//   * Variable-node values live in HBM as var[group][v][32 lanes] so every access of the warp is one full line
-//     (128 B for float, 64 B for int16, 32 B for int8): all traffic is sector-exact although the per-frame access
-//     pattern is a gather.
+// B200 mapping ("lane = frames"): a warp owns a group of 32*NF frames and walks the checks in order; lane l holds
+// frames l, 32+l, ... of the group (NF of them, so every access is one NF-wide vector per lane).
+//   * Variable-node values live in HBM as var[group][v][lane][NF]: every access of the warp is one contiguous chunk of
+//     32*NF*sizeof(R) bytes (256 B for float).  The access pattern per frame is a gather, so HBM sees random chunks;
+//     measured (profiles/r1_membench_random_rmw.txt) random read-modify-write of 128 B chunks tops out near 4.5 TB/s
+//     on this part and 256 B chunks near 5.7 TB/s, which is why NF = 2 for float.
+//   * Two checks sharing an information variable are never closer than 52 checks apart in these codes
+//     (LdpcTables::min_reuse_distance), so the values of check c+1 can be requested before check c is computed: the
+//     check loop is software-pipelined over two register sets, loads of the next check in flight during the arithmetic
+//     of the current one.  Only the parity-chain value var[K+c] links consecutive checks, and that one is carried in a
+//     register.
+//   * The per-check index rows (and "last update" masks) sit in shared memory, loaded once per persistent CTA.
 //   * Check-to-variable messages are NOT stored per edge.  Per check and frame we keep the two output magnitudes,
 //     one sign bit and one "|t| == min1" bit per edge (16 B) — the reference's output rule is value-equality based,
 //     so this reconstructs every message exactly.  Iteration 0 reads no check state at all (messages are zero).
-//   * The parity-chain value var[K+c] produced by check c is carried to check c+1 in a register.
-//   * Hard decisions are kept bit-sliced across the 32 frames: hd[group][v] is a 32-bit word written with one
-//     __ballot_sync per variable update, so the syndrome test after an iteration is E word-XORs per warp instead of
-//     E loads per frame, and the BCH stage consumes the same words directly.
+//   * Hard decisions are kept bit-sliced across 32 frames: hd[subgroup][v] is a 32-bit word written with one
+//     __ballot_sync when a variable receives its last update of the iteration, so the syndrome test after an
+//     iteration is E word-XORs per warp instead of E loads per frame, and the BCH stage consumes the same words.
 //   * A lane whose frame has converged stops writing; its bits were snapshotted into out_hd at that moment.
-// The kernel is HBM-bound: algorithmic bytes per frame and iteration = 8 B * information edges + 8 B * M (parity
-// r/w) + 32 B * M (check state r/w)   (float).
+//   * Groups are handed to warps through an atomic queue (persistent CTAs, one per SM).
+// The kernel is HBM-bound on message passing: bytes per frame and iteration = 2*sizeof(R)*(E_info + M) + 32*M
+// (DESIGN.md §5).
 #include <cfloat>
 #include <cstdint>
+#include <cstring>
 #include <cuda_runtime.h>
 
 #include "kernels.h"
@@ -55,6 +64,9 @@ struct Arith<float>
         return __float_as_uint(a);
     }
     __device__ static void unpack(unsigned lo, unsigned hi, C& a, C& b) { a = __uint_as_float(lo), b = __uint_as_float(hi); }
+    // element j of a raw vector of NF values / its inverse
+    __device__ static C from_raw(const uint32_t* w, int j) { return __uint_as_float(w[j]); }
+    __device__ static void to_raw(uint32_t* w, int j, C v) { w[j] = __float_as_uint(v); }
 };
 
 // Integer R: C++ integral promotion to int, truncation back to R on every store (wraps), exactly like the
@@ -63,6 +75,8 @@ template<typename R>
 struct ArithInt
 {
     using C = int;
+    static constexpr int BITS = 8 * (int)sizeof(R);
+    static constexpr int PER = 32 / BITS; // values per raw word
     __device__ static C wrap(int x) { return (int)(R)x; }
     __device__ static C max_value() { return sizeof(R) == 2 ? 32767 : 127; }
     __device__ static C sub(C a, C b) { return wrap(a - b); }
@@ -88,6 +102,13 @@ struct ArithInt
         return ((unsigned)a & 0xffffu) | ((unsigned)b << 16);
     }
     __device__ static void unpack(unsigned lo, unsigned, C& a, C& b) { a = (int)(short)(lo & 0xffffu), b = (int)(short)(lo >> 16); }
+    __device__ static C from_raw(const uint32_t* w, int j) { return (int)(R)(w[j / PER] >> ((j % PER) * BITS)); }
+    __device__ static void to_raw(uint32_t* w, int j, C v)
+    {
+        const uint32_t m = (BITS == 32) ? 0xffffffffu : ((1u << (BITS % 32)) - 1u);
+        if (j % PER == 0) w[j / PER] = 0;
+        w[j / PER] |= ((uint32_t)v & m) << ((j % PER) * BITS);
+    }
 };
 template<>
 struct Arith<int16_t> : ArithInt<int16_t>
@@ -98,211 +119,343 @@ struct Arith<int8_t> : ArithInt<int8_t>
 {
 };
 
-template<typename R>
-__device__ __forceinline__ typename Arith<R>::C
-ld_var(const R* p)
+// NF consecutive values of R as one 4/8/16-byte global access
+template<int BYTES>
+struct RawVec;
+template<>
+struct RawVec<4>
 {
-    return (typename Arith<R>::C)__ldcg(p);
-}
-template<typename R>
-__device__ __forceinline__ void
-st_var(R* p, typename Arith<R>::C v)
+    using T = uint32_t;
+};
+template<>
+struct RawVec<8>
 {
-    __stcg(p, (R)v);
-}
+    using T = uint2;
+};
+template<>
+struct RawVec<16>
+{
+    using T = uint4;
+};
 
 // ---------------------------------------------------------------------------------------------- the decoder
-template<typename R, int DI>
-__global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32) ldpc_decode_kernel(const LdpcLaunch a)
+template<typename R, int DI, int NF>
+struct CheckRegs
+{
+    typename RawVec<sizeof(R) * NF>::T v[DI + 1]; // information variables of the check, then var[K+c]
+    uint4 st[NF];                                 // compressed check state of the previous iteration
+};
+
+template<typename R, int DI, int NF>
+__global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kernel(const LdpcLaunch a)
 {
     using A = Arith<R>;
     using C = typename A::C;
-    constexpr int DP = (DI + 7) / 8 * 8; // row stride of the index table
+    using Raw = typename RawVec<sizeof(R) * NF>::T;
+    constexpr int NW = sizeof(Raw) / 4;  // 32-bit words per raw vector
     constexpr int D = DI + 2;            // edges per check incl. the two parity edges (bit DI = in, DI+1 = out)
+    constexpr int IW = (DI + 1) / 2;     // u32 words per index row
+    constexpr size_t VSTRIDE = 32 * NF;  // elements of R between consecutive variables
+
+    extern __shared__ uint32_t smem[];
+    const int K = a.K, M = a.M;
+    uint32_t* s_idx = smem;                    // [M][IW]
+    uint32_t* s_last = smem + (size_t)M * IW;  // [M]
+    for (int i = threadIdx.x; i < M * IW; i += blockDim.x)
+        s_idx[i] = a.idx32[i];
+    for (int i = threadIdx.x; i < M; i += blockDim.x)
+        s_last[i] = a.last[i];
+    __syncthreads();
 
     const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * LDPC_WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (g >= a.n_groups) return;
 
-    R* __restrict__ var = (R*)a.var + (size_t)g * N_LDPC * 32 + lane;
-    uint4* __restrict__ cn = a.cn + (size_t)g * a.M * 32 + lane;
-    uint32_t* __restrict__ hd = a.hd + (size_t)g * N_LDPC;
-    uint32_t* __restrict__ out_hd = a.out_hd + (size_t)g * N_LDPC;
-    const uint16_t* __restrict__ idx = a.idx;
-    const int K = a.K, M = a.M;
-
-    const int frame = g * 32 + lane;
-    unsigned active = __ballot_sync(FULL, frame < a.n_frames);
-    unsigned done = 0;   // lanes whose result is already in out_hd
-    unsigned failed = 0; // per-lane: syndrome non-zero at its last iteration
-    int my_iters = 0;
-
-    // hard decisions of the channel values (needed only if n_ite == 0 is ever allowed; also primes hd for reads)
-    for (int ite = 0; ite < a.n_ite && active; ite++)
+    for (;;)
     {
-        const bool mine = (active >> lane) & 1;
-        C chain = A::max_value(); // var[K+c-1] after check c-1; for c = 0 a neutral dummy edge
+        int g = 0;
+        if (lane == 0) g = atomicAdd(a.queue, 1);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= a.n_groups) break;
 
-        for (int c = 0; c < M; c++)
+        R* __restrict__ var = (R*)a.var + (size_t)g * N_LDPC * VSTRIDE + lane * NF;
+        uint4* __restrict__ cn = a.cn + (size_t)g * M * NF * 32 + lane;
+        uint32_t* __restrict__ hd = a.hd + (size_t)g * NF * N_LDPC;
+        uint32_t* __restrict__ out_hd = a.out_hd + (size_t)g * NF * N_LDPC;
+
+        unsigned active[NF], done[NF], failed[NF];
+        int my_iters[NF];
+        bool any_active = false;
+#pragma unroll
+        for (int j = 0; j < NF; j++)
         {
-            // ---- this check's information-variable indices (warp-uniform 16-byte loads)
-            uint32_t iw[DP / 2];
-            const uint4* ip = reinterpret_cast<const uint4*>(idx + (size_t)c * DP);
-#pragma unroll
-            for (int k = 0; k < DP / 8; k++)
-            {
-                const uint4 q = __ldg(ip + k);
-                iw[4 * k + 0] = q.x, iw[4 * k + 1] = q.y, iw[4 * k + 2] = q.z, iw[4 * k + 3] = q.w;
-            }
-            // ---- previous messages of this check, compressed (none yet in iteration 0)
-            uint4 st = make_uint4(0u, 0u, 0u, 0u);
-            if (ite > 0) st = __ldcg(cn + (size_t)c * 32);
-            C o1, o2;
-            A::unpack(st.x, st.y, o1, o2);
-            const unsigned osg = st.z, oeq = st.w;
-
-            // ---- pass 1: t = var - msg, running sign / min1 / min2 (Update_rule_MS.hxx:57-67)
-            C t[D];
-            unsigned sacc = 0;
-            C min1 = A::max_value(), min2 = A::max_value();
-#pragma unroll
-            for (int i = 0; i < D; i++)
-            {
-                C v;
-                if (i < DI)
-                {
-                    const unsigned vi = (iw[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-                    v = ld_var<R>(var + (size_t)vi * 32);
-                }
-                else if (i == DI)
-                    v = chain;
-                else
-                    v = ld_var<R>(var + (size_t)(K + c) * 32);
-                const C m = A::with_sign(((oeq >> i) & 1u) ? o1 : o2, (osg >> i) & 1u);
-                C ti = A::sub(v, m);
-                if (i == DI && c == 0) ti = A::max_value(); // check 0 has no incoming chain edge
-                t[i] = ti;
-                const C ab = A::absv(ti);
-                sacc ^= A::neg(ti);
-                min2 = A::vmin(min2, A::vmax(ab, min1));
-                min1 = A::vmin(min1, ab);
-            }
-            // ---- normalise, clamp (Update_rule_NMS.hxx:100-106)
-            const C c1 = A::vmax((C)0, A::normalize(min2, a.norm, a.k8));
-            const C c2 = A::vmax((C)0, A::normalize(min1, a.norm, a.k8));
-
-            // ---- pass 2: new messages and variable values (Update_rule_MS.hxx:82-92, ...layered.hxx:198-203)
-            unsigned nsg = 0, neq = 0;
-#pragma unroll
-            for (int i = 0; i < D; i++)
-            {
-                const C ti = t[i];
-                const unsigned e = (A::absv(ti) == min1);
-                const unsigned s = sacc ^ A::neg(ti);
-                const C nv = A::add(ti, A::with_sign(e ? c1 : c2, s));
-                neq |= e << i;
-                nsg |= s << i;
-                int vi;
-                if (i < DI)
-                    vi = (iw[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-                else if (i == DI)
-                    vi = K + c - 1;
-                else
-                    vi = K + c;
-                if (i == DI + 1)
-                {
-                    chain = nv; // consumed (and stored) by check c+1; only the last check must store it itself
-                    if (c != M - 1) continue;
-                }
-                if (i == DI && c == 0) continue;
-                if (mine) st_var<R>(var + (size_t)vi * 32, nv);
-                const unsigned w = __ballot_sync(FULL, A::lt0(nv));
-                if (lane == 0) __stcg(hd + vi, w);
-            }
-            if (mine)
-            {
-                unsigned hi;
-                const unsigned lo = A::pack(c1, c2, hi);
-                __stcg(cn + (size_t)c * 32, make_uint4(lo, hi, nsg, neq));
-            }
+            const int frame = (g * NF + j) * 32 + lane;
+            active[j] = __ballot_sync(FULL, frame < a.n_frames);
+            done[j] = failed[j] = 0;
+            my_iters[j] = 0;
+            any_active |= active[j] != 0;
         }
-        my_iters += mine ? 1 : 0;
 
-        // ---- syndrome on the bit-sliced hard decisions: lane j tests checks j, j+32, ...
-        __syncwarp();
-        unsigned unsat = 0;
-        for (int c = lane; c < M; c += 32)
+        for (int ite = 0; ite < a.n_ite && any_active; ite++)
         {
-            unsigned p = __ldcg(hd + K + c);
-            if (c > 0) p ^= __ldcg(hd + K + c - 1);
-            const uint16_t* ic = idx + (size_t)c * DP;
+            bool mine[NF];
 #pragma unroll
-            for (int i = 0; i < DI; i++)
-                p ^= __ldcg(hd + ic[i]);
-            unsat |= p;
-        }
-        unsat = __reduce_or_sync(FULL, unsat);
+            for (int j = 0; j < NF; j++)
+                mine[j] = (active[j] >> lane) & 1;
+            bool mine_any = false;
+#pragma unroll
+            for (int j = 0; j < NF; j++)
+                mine_any |= mine[j];
 
-        const bool last = (ite == a.n_ite - 1);
-        unsigned fin = active & ~unsat;
-        if (!a.early_stop) fin = 0;
-        if (last) fin = active;
-        if (fin)
-        {
-            // snapshot the finishing lanes' hard decisions
-            for (int v = lane; v < N_LDPC; v += 32)
+            C chain[NF]; // var[K+c-1] after check c-1; for c = 0 a neutral dummy edge
+#pragma unroll
+            for (int j = 0; j < NF; j++)
+                chain[j] = A::max_value();
+
+            // ---- requests everything check c reads from HBM (hazard-free ahead of time, see header)
+            auto issue = [&](CheckRegs<R, DI, NF>& r, int c) {
+                const uint32_t* row = s_idx + c * IW;
+#pragma unroll
+                for (int i = 0; i < DI; i++)
+                {
+                    const unsigned vi = (row[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+                    r.v[i] = __ldcg(reinterpret_cast<const Raw*>(var + (size_t)vi * VSTRIDE));
+                }
+                r.v[DI] = __ldcg(reinterpret_cast<const Raw*>(var + (size_t)(K + c) * VSTRIDE));
+#pragma unroll
+                for (int j = 0; j < NF; j++)
+                    r.st[j] = ite > 0 ? __ldcg(cn + (size_t)(c * NF + j) * 32) : make_uint4(0u, 0u, 0u, 0u);
+            };
+
+            // ---- check c on the values in r (Update_rule_MS.hxx:57-92, Update_rule_NMS.hxx:100-106, ...layered.hxx:198-203)
+            auto compute = [&](CheckRegs<R, DI, NF>& r, int c) {
+                const uint32_t* row = s_idx + c * IW;
+                const uint32_t lastm = s_last[c];
+                C t[D][NF];
+                C min1[NF], c1[NF], c2[NF];
+                unsigned sacc[NF];
+#pragma unroll
+                for (int j = 0; j < NF; j++)
+                {
+                    C o1, o2;
+                    A::unpack(r.st[j].x, r.st[j].y, o1, o2);
+                    const unsigned osg = r.st[j].z, oeq = r.st[j].w;
+                    unsigned sa = 0;
+                    C m1 = A::max_value(), m2 = A::max_value();
+#pragma unroll
+                    for (int i = 0; i < D; i++)
+                    {
+                        C v;
+                        if (i < DI)
+                        {
+                            uint32_t w[NW];
+                            memcpy(w, &r.v[i], sizeof(Raw));
+                            v = A::from_raw(w, j);
+                        }
+                        else if (i == DI)
+                            v = chain[j];
+                        else
+                        {
+                            uint32_t w[NW];
+                            memcpy(w, &r.v[DI], sizeof(Raw));
+                            v = A::from_raw(w, j);
+                        }
+                        const C m = A::with_sign(((oeq >> i) & 1u) ? o1 : o2, (osg >> i) & 1u);
+                        C ti = A::sub(v, m);
+                        if (i == DI && c == 0) ti = A::max_value(); // check 0 has no incoming chain edge
+                        t[i][j] = ti;
+                        const C ab = A::absv(ti);
+                        sa ^= A::neg(ti);
+                        m2 = A::vmin(m2, A::vmax(ab, m1));
+                        m1 = A::vmin(m1, ab);
+                    }
+                    min1[j] = m1, sacc[j] = sa;
+                    c1[j] = A::vmax((C)0, A::normalize(m2, a.norm, a.k8));
+                    c2[j] = A::vmax((C)0, A::normalize(m1, a.norm, a.k8));
+                }
+
+                unsigned nsg[NF], neq[NF];
+#pragma unroll
+                for (int j = 0; j < NF; j++)
+                    nsg[j] = neq[j] = 0;
+#pragma unroll
+                for (int i = 0; i < D; i++)
+                {
+                    C nv[NF];
+#pragma unroll
+                    for (int j = 0; j < NF; j++)
+                    {
+                        const C ti = t[i][j];
+                        const unsigned e = (A::absv(ti) == min1[j]);
+                        const unsigned s = sacc[j] ^ A::neg(ti);
+                        nv[j] = A::add(ti, A::with_sign(e ? c1[j] : c2[j], s));
+                        neq[j] |= e << i;
+                        nsg[j] |= s << i;
+                    }
+                    int vi;
+                    bool ballot;
+                    if (i < DI)
+                    {
+                        vi = (row[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+                        ballot = (lastm >> i) & 1u;
+                    }
+                    else if (i == DI)
+                    {
+                        if (c == 0) continue;
+                        vi = K + c - 1;
+                        ballot = true; // check c is the last one to touch parity variable K+c-1
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int j = 0; j < NF; j++)
+                            chain[j] = nv[j]; // consumed (and stored) by check c+1; only the last check stores it itself
+                        if (c != M - 1) continue;
+                        vi = K + c;
+                        ballot = true;
+                    }
+                    if (mine_any)
+                    { // a finished frame sharing the lane gets a value it never reads again
+                        uint32_t w[NW];
+#pragma unroll
+                        for (int j = 0; j < NF; j++)
+                            A::to_raw(w, j, nv[j]);
+                        Raw out;
+                        memcpy(&out, w, sizeof(Raw));
+                        __stcg(reinterpret_cast<Raw*>(var + (size_t)vi * VSTRIDE), out);
+                    }
+                    if (ballot)
+                    {
+#pragma unroll
+                        for (int j = 0; j < NF; j++)
+                        {
+                            const unsigned w = __ballot_sync(FULL, A::lt0(nv[j]));
+                            if (lane == 0) __stcg(hd + (size_t)j * N_LDPC + vi, w);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NF; j++)
+                    if (mine[j])
+                    {
+                        unsigned hi;
+                        const unsigned lo = A::pack(c1[j], c2[j], hi);
+                        __stcg(cn + (size_t)(c * NF + j) * 32, make_uint4(lo, hi, nsg[j], neq[j]));
+                    }
+            };
+
+            CheckRegs<R, DI, NF> ra, rb;
+            issue(ra, 0);
+            for (int c = 0; c < M; c += 2) // M is even for both codes
             {
-                const unsigned w = __ldcg(hd + v);
-                const unsigned o = done ? __ldcg(out_hd + v) : 0u;
-                __stcg(out_hd + v, (o & done) | (w & fin));
+                issue(rb, c + 1);
+                compute(ra, c);
+                if (c + 2 < M) issue(ra, c + 2);
+                compute(rb, c + 1);
+            }
+#pragma unroll
+            for (int j = 0; j < NF; j++)
+                my_iters[j] += mine[j] ? 1 : 0;
+
+            // ---- syndrome on the bit-sliced hard decisions: lane l tests checks l, l+32, ...
+            __syncwarp();
+            unsigned unsat[NF];
+#pragma unroll
+            for (int j = 0; j < NF; j++)
+                unsat[j] = 0;
+            for (int c = lane; c < M; c += 32)
+            {
+                const uint32_t* row = s_idx + c * IW;
+#pragma unroll
+                for (int j = 0; j < NF; j++)
+                {
+                    const uint32_t* hj = hd + (size_t)j * N_LDPC;
+                    unsigned p = __ldcg(hj + K + c);
+                    if (c > 0) p ^= __ldcg(hj + K + c - 1);
+#pragma unroll
+                    for (int i = 0; i < DI; i++)
+                        p ^= __ldcg(hj + ((row[i >> 1] >> ((i & 1) * 16)) & 0xffffu));
+                    unsat[j] |= p;
+                }
+            }
+            const bool last = (ite == a.n_ite - 1);
+            any_active = false;
+#pragma unroll
+            for (int j = 0; j < NF; j++)
+            {
+                unsat[j] = __reduce_or_sync(FULL, unsat[j]);
+                unsigned fin = active[j] & ~unsat[j];
+                if (!a.early_stop) fin = 0;
+                if (last) fin = active[j];
+                if (fin)
+                {
+                    // snapshot the finishing lanes' hard decisions
+                    const uint32_t* hj = hd + (size_t)j * N_LDPC;
+                    uint32_t* oj = out_hd + (size_t)j * N_LDPC;
+                    for (int v = lane; v < N_LDPC; v += 32)
+                    {
+                        const unsigned w = __ldcg(hj + v);
+                        const unsigned o = done[j] ? __ldcg(oj + v) : 0u;
+                        __stcg(oj + v, (o & done[j]) | (w & fin));
+                    }
+                    failed[j] |= fin & unsat[j];
+                    done[j] |= fin;
+                    active[j] &= ~fin;
+                }
+                any_active |= active[j] != 0;
             }
             __syncwarp();
-            failed |= fin & unsat;
-            done |= fin;
-            active &= ~fin;
         }
-    }
 
-    if (frame < a.n_frames)
-    {
-        const bool ok = !((failed >> lane) & 1);
-        if (a.cwd) a.cwd[frame] = (int8_t)ok;
-        if (a.n_iter) a.n_iter[frame] = my_iters;
-        // stats: iterations and failures (one atomic per warp)
-    }
-    const unsigned valid = __ballot_sync(FULL, frame < a.n_frames);
-    int it_sum = __reduce_add_sync(FULL, frame < a.n_frames ? my_iters : 0);
-    if (lane == 0 && a.stats)
-    {
-        atomicAdd(a.stats + STAT_FRAMES, (unsigned long long)__popc(valid));
-        atomicAdd(a.stats + STAT_LDPC_ITERS, (unsigned long long)it_sum);
-        atomicAdd(a.stats + STAT_LDPC_FAIL, (unsigned long long)__popc(failed & valid));
+        int it_sum = 0, n_valid = 0, n_failed = 0;
+#pragma unroll
+        for (int j = 0; j < NF; j++)
+        {
+            const int frame = (g * NF + j) * 32 + lane;
+            const bool valid = frame < a.n_frames;
+            if (valid)
+            {
+                const bool ok = !((failed[j] >> lane) & 1);
+                if (a.cwd) a.cwd[frame] = (int8_t)ok;
+                if (a.n_iter) a.n_iter[frame] = my_iters[j];
+            }
+            const unsigned vm = __ballot_sync(FULL, valid);
+            it_sum += __reduce_add_sync(FULL, valid ? my_iters[j] : 0);
+            n_valid += __popc(vm);
+            n_failed += __popc(failed[j] & vm);
+        }
+        if (lane == 0 && a.stats)
+        {
+            atomicAdd(a.stats + STAT_FRAMES, (unsigned long long)n_valid);
+            atomicAdd(a.stats + STAT_LDPC_ITERS, (unsigned long long)it_sum);
+            atomicAdd(a.stats + STAT_LDPC_FAIL, (unsigned long long)n_failed);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------- layout kernels
-// frame-major LLRs [F][16200] -> var[group][v][lane]; frames past n_frames are zero-filled.
+// frame-major LLRs [F][16200] -> var[group][v][lane][NF] (frame = (group*NF + j)*32 + lane); frames past n_frames = 0.
+// One block per (32 variables, 32-frame subgroup).
 template<typename R>
 __global__ void
-pack_llr_kernel(const R* __restrict__ in, R* __restrict__ var, int n_frames)
+pack_llr_kernel(const R* __restrict__ in, R* __restrict__ var, int n_frames, int nf)
 {
     __shared__ R tile[32][33];
-    const int g = blockIdx.y, v0 = blockIdx.x * 32;
+    const int sg = blockIdx.y, v0 = blockIdx.x * 32; // sg = 32-frame subgroup index = group*nf + j
+    const int g = sg / nf, j = sg % nf;
     const int x = threadIdx.x, y = threadIdx.y;
-    for (int j = y; j < 32; j += blockDim.y)
+    for (int k = y; k < 32; k += blockDim.y)
     {
-        const int f = g * 32 + j, v = v0 + x;
-        tile[j][x] = (f < n_frames && v < N_LDPC) ? in[(size_t)f * N_LDPC + v] : (R)0;
+        const int f = sg * 32 + k, v = v0 + x;
+        tile[k][x] = (f < n_frames && v < N_LDPC) ? in[(size_t)f * N_LDPC + v] : (R)0;
     }
     __syncthreads();
-    for (int j = y; j < 32; j += blockDim.y)
+    for (int k = y; k < 32; k += blockDim.y)
     {
-        const int v = v0 + j;
-        if (v < N_LDPC) var[((size_t)g * N_LDPC + v) * 32 + x] = tile[x][j];
+        const int v = v0 + k;
+        if (v < N_LDPC) var[(((size_t)g * N_LDPC + v) * 32 + x) * nf + j] = tile[x][k];
     }
 }
 
-// bit-sliced words [group][stride] -> int32 bits [F][K] (first K variables)
+// bit-sliced words [subgroup][stride] -> int32 bits [F][K] (first K variables)
 __global__ void
 unpack_bits_kernel(const uint32_t* __restrict__ words, int32_t* __restrict__ out, int stride, int K, int n_frames)
 {
@@ -318,7 +471,7 @@ unpack_bits_kernel(const uint32_t* __restrict__ words, int32_t* __restrict__ out
     }
 }
 
-// int32 bits [F][N] -> bit-sliced words [group][stride]
+// int32 bits [F][N] -> bit-sliced words [subgroup][stride]
 __global__ void
 pack_bits_kernel(const int32_t* __restrict__ in, uint32_t* __restrict__ words, int stride, int N, int n_frames)
 {
@@ -340,18 +493,35 @@ pack_bits_kernel(const int32_t* __restrict__ in, uint32_t* __restrict__ words, i
 } // namespace
 
 // ---------------------------------------------------------------------------------------------- launchers
-template<typename R>
+int
+ldpc_frames_per_lane(int precision)
+{
+    return precision == 0 ? 2 : precision == 1 ? 2 : 4;
+}
+
+template<typename R, int DI, int NF>
+static cudaError_t
+launch_ldpc_k(const LdpcLaunch& a, cudaStream_t s)
+{
+    auto k = ldpc_decode_kernel<R, DI, NF>;
+    const size_t smem = ((size_t)a.M * ((DI + 1) / 2) + a.M) * sizeof(uint32_t);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); // per device
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(a.queue, 0, sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    const int want = (a.n_groups + LDPC_WARPS_PER_BLOCK - 1) / LDPC_WARPS_PER_BLOCK;
+    const int blocks = want < a.n_sms ? want : a.n_sms;
+    k<<<blocks, LDPC_WARPS_PER_BLOCK * 32, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template<typename R, int NF>
 static cudaError_t
 launch_ldpc_t(const LdpcLaunch& a, cudaStream_t s)
 {
-    const int blocks = (a.n_groups + LDPC_WARPS_PER_BLOCK - 1) / LDPC_WARPS_PER_BLOCK;
-    if (a.d_info == 25)
-        ldpc_decode_kernel<R, 25><<<blocks, LDPC_WARPS_PER_BLOCK * 32, 0, s>>>(a);
-    else if (a.d_info == 9)
-        ldpc_decode_kernel<R, 9><<<blocks, LDPC_WARPS_PER_BLOCK * 32, 0, s>>>(a);
-    else
-        return cudaErrorInvalidValue;
-    return cudaGetLastError();
+    if (a.d_info == 25) return launch_ldpc_k<R, 25, NF>(a, s);
+    if (a.d_info == 9) return launch_ldpc_k<R, 9, NF>(a, s);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t
@@ -359,9 +529,9 @@ launch_ldpc_decode(const LdpcLaunch& a, int precision, cudaStream_t s)
 {
     switch (precision)
     {
-        case 0: return launch_ldpc_t<float>(a, s);
-        case 1: return launch_ldpc_t<int16_t>(a, s);
-        case 2: return launch_ldpc_t<int8_t>(a, s);
+        case 0: return launch_ldpc_t<float, 2>(a, s);
+        case 1: return launch_ldpc_t<int16_t, 2>(a, s);
+        case 2: return launch_ldpc_t<int8_t, 4>(a, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -369,13 +539,14 @@ launch_ldpc_decode(const LdpcLaunch& a, int precision, cudaStream_t s)
 cudaError_t
 launch_pack_llr(const void* in, void* var, int precision, int n_frames, cudaStream_t s)
 {
-    const int groups = (n_frames + 31) / 32;
-    const dim3 grid((N_LDPC + 31) / 32, groups), block(32, 8);
+    const int nf = ldpc_frames_per_lane(precision);
+    const int groups = (n_frames + 32 * nf - 1) / (32 * nf);
+    const dim3 grid((N_LDPC + 31) / 32, groups * nf), block(32, 8);
     switch (precision)
     {
-        case 0: pack_llr_kernel<float><<<grid, block, 0, s>>>((const float*)in, (float*)var, n_frames); break;
-        case 1: pack_llr_kernel<int16_t><<<grid, block, 0, s>>>((const int16_t*)in, (int16_t*)var, n_frames); break;
-        case 2: pack_llr_kernel<int8_t><<<grid, block, 0, s>>>((const int8_t*)in, (int8_t*)var, n_frames); break;
+        case 0: pack_llr_kernel<float><<<grid, block, 0, s>>>((const float*)in, (float*)var, n_frames, nf); break;
+        case 1: pack_llr_kernel<int16_t><<<grid, block, 0, s>>>((const int16_t*)in, (int16_t*)var, n_frames, nf); break;
+        case 2: pack_llr_kernel<int8_t><<<grid, block, 0, s>>>((const int8_t*)in, (int8_t*)var, n_frames, nf); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

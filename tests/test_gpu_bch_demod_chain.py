@@ -220,5 +220,5 @@ def test_errors_are_reported_not_swallowed():
     with pytest.raises(ValueError):
         dec.decode_siho(np.zeros(10, np.float32), np.zeros(32, np.int8), np.zeros((32, dec.K), np.int32))
     with pytest.raises(ValueError):
-        dec.set_n_frames(64)
+        dec.set_n_frames(h.info["max_frames"] + 1)
     h.close()

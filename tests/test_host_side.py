@@ -1,0 +1,164 @@
+"""CPU suite: the C-ABI library loads and exports what include/dvbs2_cuda.h declares; host-side logic (flags, sharding,
+counter reduction over a world_size-2 gloo group); loud failure without a GPU.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    from dvbs2_b200 import capi
+
+    if not os.path.exists(capi.LIB_PATH):
+        import subprocess
+
+        subprocess.check_call(["make", "-j8", "-C", os.path.join(ROOT, "dvbs2_b200", "csrc")])
+    return capi.load()
+
+
+def test_library_exports_every_declared_symbol():
+    from dvbs2_b200 import capi
+
+    lib = _lib()
+    hdr = open(os.path.join(ROOT, "include", "dvbs2_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(dvbs2_cuda_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(capi.SYMBOLS) == declared  # the ctypes binding covers the whole header
+
+
+def test_structs_match_header_layout():
+    from dvbs2_b200 import capi
+
+    lib = _lib()
+    assert C.sizeof(capi.Cfg) == 16 * 4 and C.sizeof(capi.Info) == 9 * 4 and C.sizeof(capi.Stats) == 6 * 8
+    assert C.sizeof(capi.Timers) == 10 * 8 and C.sizeof(capi.Monitor) == 3 * 8
+    cfg = capi.Cfg()
+    lib.dvbs2_cuda_default_cfg(C.byref(cfg))
+    assert (cfg.modcod, cfg.n_ite, cfg.norm, cfg.precision, cfg.early_stop) == (0, 10, 1.0, 0, 1)
+    assert (cfg.quant_bits, cfg.quant_dec) == (6, 2)  # AFF3CT's LDPC quantiser defaults (Launcher/Code/LDPC/LDPC.cpp:58-62)
+    assert lib.dvbs2_cuda_strerror(0) == b"success" and b"CUDA" in lib.dvbs2_cuda_strerror(-2)
+    assert lib.dvbs2_cuda_strerror(-3) and lib.dvbs2_cuda_strerror(-99) == b"unknown status"
+
+
+def test_argument_validation_needs_no_gpu():
+    from dvbs2_b200 import capi
+
+    lib = _lib()
+    h = C.c_void_p()
+    cfg = capi.Cfg()
+    lib.dvbs2_cuda_default_cfg(C.byref(cfg))
+    assert lib.dvbs2_cuda_create(None, C.byref(h)) == capi.ERR_INVALID
+    for field, bad in (("modcod", 7), ("n_ite", 0), ("precision", 3), ("max_frames", 0), ("norm", 1.5), ("norm", 0.0)):
+        c2 = capi.Cfg.from_buffer_copy(cfg)
+        setattr(c2, field, bad)
+        assert lib.dvbs2_cuda_create(C.byref(c2), C.byref(h)) == capi.ERR_INVALID, field
+    c2 = capi.Cfg.from_buffer_copy(cfg)
+    c2.precision, c2.norm = capi.PREC["i16"], 0.3  # integer decoders only know k/8 (Update_rule_NMS.hxx:14-39)
+    assert lib.dvbs2_cuda_create(C.byref(c2), C.byref(h)) == capi.ERR_INVALID
+    assert lib.dvbs2_cuda_sync(None) == capi.ERR_INVALID and lib.dvbs2_cuda_destroy(None) == capi.OK
+
+
+def test_no_cpu_fallback_without_a_device():
+    """On a host without a CUDA device the product path must fail loudly, never fall back to the oracle."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("this host has a GPU")
+    from dvbs2_b200 import Handle, capi
+
+    _lib()
+    assert capi.load().dvbs2_cuda_device_count() == 0
+    with pytest.raises(capi.Dvbs2CudaError) as e:
+        Handle()
+    assert e.value.status == capi.ERR_CUDA
+    import dvbs2_b200
+
+    src = "".join(open(os.path.join(ROOT, "dvbs2_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "dvbs2_b200"))
+                  if f.endswith(".py"))
+    assert "import oracle" not in src and "from oracle" not in src and dvbs2_b200.__name__ == "dvbs2_b200"
+
+
+def test_factory_flags_follow_the_reference():
+    from dvbs2_b200.factory import DVBS2
+
+    p = DVBS2(["--mod-cod", "8PSK-S_3/5", "--dec-implem", "NMS", "--dec-ite", "10", "--dec-simd", "INTER", "-F", "16"])
+    assert (p.modcod, p.ldpc_implem, p.ldpc_nite, p.n_frames, p.norm, p.precision) == ("8PSK-S_3/5", "NMS", 10, 16, 1.0, "f32")
+    assert DVBS2([]).ldpc_nite == 50  # DVBS2.cpp:135 default
+    assert DVBS2(["--dec-implem", "MS", "--dec-norm", "0.75"]).norm == 1.0
+    assert DVBS2(["--dec-implem", "NMS", "--dec-norm", "0.75", "--dec-prec", "16"]).precision == "i16"
+    with pytest.raises(ValueError):
+        DVBS2(["--dec-implem", "SPA"])
+    with pytest.raises(SystemExit):
+        DVBS2(["--mod-cod", "32APSK-S_9/10"])
+    with pytest.raises(ValueError):
+        DVBS2(["-F", "0"])
+
+
+def test_sigma_formula_matches_oracle():
+    from dvbs2_b200 import synth
+    from oracle.oracle import MODCODS, ebn0_to_sigma
+
+    for m in MODCODS:
+        for e in (0.0, 2.2, 4.0, 7.5):
+            assert abs(synth.ebn0_to_sigma(m, e) - ebn0_to_sigma(m, e)) < 1e-12
+        assert synth.MODCODS[m]["K_bch"] == MODCODS[m]["K_bch"] and synth.MODCODS[m]["bps"] == MODCODS[m]["bps"]
+    assert abs(synth.ebn0_to_sigma("QPSK-S_8/9", 4.0) - 0.3366) < 1e-4
+
+
+def test_shard_frames():
+    from dvbs2_b200.dist import shard_frames
+
+    for n in (0, 1, 7, 8, 100, 75776):
+        for w in (1, 2, 3, 8):
+            parts = [shard_frames(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and sum(c for _, c in parts) == n
+            assert all(parts[i][0] + parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+    with pytest.raises(ValueError):
+        shard_frames(10, 2, 2)
+
+
+def _rank_main(rank, world, port, out):
+    import torch.distributed as dist
+
+    from dvbs2_b200.dist import Monitor_BFER_reduction, reduce_counters, reduce_max, shard_frames
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    first, cnt = shard_frames(1001, rank, world)
+    # each rank "decodes" its shard: frame f has f % 7 bit errors
+    f = np.arange(first, first + cnt)
+    local = {"n_frames": cnt, "n_be": int((f % 7).sum()), "n_fe": int((f % 7 != 0).sum())}
+    tot = reduce_counters(local)
+    mon = Monitor_BFER_reduction(max_fe=800)
+    mon.update(local)
+    t = reduce_max(0.5 + rank)
+    out.put((rank, tot, mon.is_done(), mon.rates(10), t))
+    dist.destroy_process_group()
+
+
+def test_counter_reduction_world_size_2_gloo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    ps = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    f = np.arange(1001)
+    want = {"n_be": int((f % 7).sum()), "n_fe": int((f % 7 != 0).sum()), "n_frames": 1001}
+    for rank, tot, done, rates, t in res:
+        assert tot == want and done and t == 1.5
+        assert abs(rates["fer"] - want["n_fe"] / 1001) < 1e-12 and abs(rates["ber"] - want["n_be"] / 10010) < 1e-12
