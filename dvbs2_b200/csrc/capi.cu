@@ -20,7 +20,7 @@ using namespace dvbs2;
 
 namespace
 {
-constexpr int N_PIPE = 3; // streams used to overlap H2D / compute / D2H in the host-buffer entry points
+constexpr int N_PIPE = 4; // streams used to overlap H2D / compute / D2H in the host-buffer entry points
 
 struct DevBuf
 {
@@ -330,9 +330,12 @@ tx_args(dvbs2_cuda_handle* h, int n_frames)
 int
 chunk_frames(const dvbs2_cuda_handle* h, int n_frames)
 {
-    int per = (n_frames + N_PIPE * 2 - 1) / (N_PIPE * 2); // ~6 chunks per call
-    per = std::max(per, 4096);                             // below this the kernels are launch/latency bound anyway
-    per = (per + 255) / 256 * 256;                         // whole decoder groups for every precision
+    // one chunk per pipeline stream: the LDPC kernel's duration hardly depends on the chunk size (a warp walks its group
+    // through every check either way), so fewer, larger chunks keep more SMs busy while copies of the other chunks — and
+    // of other module clones — proceed
+    int per = (n_frames + N_PIPE - 1) / N_PIPE;
+    per = std::max(per, 2048);
+    per = (per + 255) / 256 * 256; // whole decoder groups for every precision
     (void)h;
     return per;
 }

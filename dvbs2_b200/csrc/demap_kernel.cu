@@ -85,8 +85,8 @@ demap_frames_kernel(const DemapLaunch a, float* __restrict__ llr, int deinterlea
     __shared__ float cs[2 << BPS];
     if (threadIdx.x < (2 << BPS)) cs[threadIdx.x] = a.cstl[threadIdx.x];
     __syncthreads();
-    const int f = blockIdx.y;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.x; // frames on grid.x: batches exceed the 65535 limit of grid.y
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
     if (k >= a.n_sym) return;
     const float sg = a.sigma[f];
     const float inv = 1.0f / (2 * sg * sg);
@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(DEMAP_WARPS * 32) demap_to_var_kernel(const De
 __global__ void
 deinterleave_kernel(const float* __restrict__ itl, float* __restrict__ nat, int bps, int n_sym, int itl_cols, int itl_rev)
 {
-    const int f = blockIdx.y;
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.x;
+    const int n = blockIdx.y * blockDim.x + threadIdx.x;
     if (n >= N_LDPC) return;
     const int k = n / bps, b = n % bps;
     nat[(size_t)f * N_LDPC + natural_pos(k, b, bps, n_sym, itl_cols, itl_rev)] = itl[(size_t)f * N_LDPC + n];
@@ -165,7 +165,7 @@ quantize_kernel(const float* __restrict__ in, R* __restrict__ out, size_t n, flo
 cudaError_t
 launch_demap_frames(const DemapLaunch& a, float* llr, int deinterleave, cudaStream_t s)
 {
-    const dim3 grid((a.n_sym + 255) / 256, a.n_frames);
+    const dim3 grid(a.n_frames, (a.n_sym + 255) / 256);
     switch (a.bps)
     {
         case 2: demap_frames_kernel<2><<<grid, 256, 0, s>>>(a, llr, deinterleave); break;
@@ -208,7 +208,7 @@ cudaError_t
 launch_deinterleave(const float* itl, float* nat, int n_frames, int n_sym, int itl_cols, int itl_rev, cudaStream_t s)
 {
     const int bps = N_LDPC / n_sym;
-    const dim3 grid((N_LDPC + 255) / 256, n_frames);
+    const dim3 grid(n_frames, (N_LDPC + 255) / 256);
     deinterleave_kernel<<<grid, 256, 0, s>>>(itl, nat, bps, n_sym, itl_cols, itl_rev);
     return cudaGetLastError();
 }

@@ -322,14 +322,12 @@ __global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kern
                         memcpy(&out, w, sizeof(Raw));
                         __stcg(reinterpret_cast<Raw*>(var + (size_t)vi * VSTRIDE), out);
                     }
-                    if (ballot)
-                    {
+                    // the vote is unconditional (no divergence scaffolding around it); only the store is predicated
 #pragma unroll
-                        for (int j = 0; j < NF; j++)
-                        {
-                            const unsigned w = __ballot_sync(FULL, A::lt0(nv[j]));
-                            if (lane == 0) __stcg(hd + (size_t)j * N_LDPC + vi, w);
-                        }
+                    for (int j = 0; j < NF; j++)
+                    {
+                        const unsigned w = __ballot_sync(FULL, A::lt0(nv[j]));
+                        if (ballot && lane == 0) __stcg(hd + (size_t)j * N_LDPC + vi, w);
                     }
                 }
 #pragma unroll
@@ -342,14 +340,16 @@ __global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kern
                     }
             };
 
+            // one loop body (~27 KB of SASS, inside the 32 KB L1.5 instruction cache; the two-body ping-pong version was
+            // 52 KB and stalled on instruction fetch): rb receives check c+1 while check c is computed from ra
             CheckRegs<R, DI, NF> ra, rb;
             issue(ra, 0);
-            for (int c = 0; c < M; c += 2) // M is even for both codes
+#pragma unroll 1
+            for (int c = 0; c < M; c++)
             {
-                issue(rb, c + 1);
+                if (c + 1 < M) issue(rb, c + 1);
                 compute(ra, c);
-                if (c + 2 < M) issue(ra, c + 2);
-                compute(rb, c + 1);
+                ra = rb;
             }
 #pragma unroll
             for (int j = 0; j < NF; j++)

@@ -128,8 +128,8 @@ __global__ void __launch_bounds__(256) tx_modulate_awgn_kernel(const uint32_t* _
                                                               int itl_cols, int itl_rev, int n_frames, float sigma,
                                                               uint64_t seed)
 {
-    const int f = blockIdx.y;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.x; // frames on grid.x: batches exceed the 65535 limit of grid.y
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
     if (k == 0) cp[f] = sigma;
     if (k >= n_sym) return;
     const uint32_t* c = cw + (size_t)(f >> 5) * N_LDPC;
@@ -226,7 +226,7 @@ cudaError_t
 launch_tx_modulate_awgn(const TxLaunch& a, const float* cstl, float* sym, float* cp, int bps, int n_sym, int itl_cols,
                         int itl_rev, float sigma, uint64_t seed, cudaStream_t s)
 {
-    const dim3 grid((n_sym + 255) / 256, a.n_frames);
+    const dim3 grid(a.n_frames, (n_sym + 255) / 256);
     tx_modulate_awgn_kernel<<<grid, 256, 0, s>>>(a.cw, cstl, sym, cp, bps, n_sym, itl_cols, itl_rev, a.n_frames, sigma, seed);
     return cudaGetLastError();
 }

@@ -1,0 +1,23 @@
+"""GPU: the C++ StreamPU/AFF3CT GPU modules (dvbs2_b200/module/*.hpp) against the reference's own CPU modules, through the
+task/socket interface and inside a 2-thread spu::runtime::Sequence.  The checker binary is built in the build container by
+dvbs2_b200/module/build_check.sh (it compiles against the reference's headers) and travels with the repo snapshot."""
+import json
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "dvbs2_b200", "module", "_build", "module_check")
+
+
+@pytest.mark.parametrize("modcod,ebn0", [("QPSK-S_8/9", 3.95), ("8PSK-S_3/5", 3.9), ("16APSK-S_8/9", 7.7)])
+def test_cpp_modules_drop_in(modcod, ebn0):
+    if not os.path.exists(BIN):
+        pytest.skip("module_check was not built (needs the reference headers: dvbs2_b200/module/build_check.sh)")
+    r = subprocess.run([BIN, modcod, "32", str(ebn0)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["failures"] == 0 and d["frames"] == 192 and d["seq_frames"] == 192
+    assert d["seq_be"] == d["ref_be"] and d["seq_fe"] == d["ref_fe"] and d["demod_max_rel_err"] <= 1e-4
