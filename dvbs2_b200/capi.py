@@ -30,7 +30,7 @@ SYMBOLS = [
 class Cfg(C.Structure):
     _fields_ = [("modcod", C.c_int), ("n_ite", C.c_int), ("norm", C.c_float), ("precision", C.c_int),
                 ("early_stop", C.c_int), ("max_frames", C.c_int), ("device", C.c_int), ("quant_bits", C.c_int),
-                ("quant_dec", C.c_int), ("reserved", C.c_int * 7)]
+                ("quant_dec", C.c_int), ("no_compaction", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class Info(C.Structure):

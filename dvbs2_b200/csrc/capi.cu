@@ -72,6 +72,9 @@ struct dvbs2_cuda_handle
     BchDevTables bch{};
     // decoder state
     DevBuf var, cn, hd, out_hd, rem, nz, cwd_ldpc, cwd_bch, nit, stats;
+    // frame compaction: slots [max_frames, max_frames + ext_cap) of var/cn/hd/out_hd hold the survivors of round 1
+    DevBuf surv_mask, surv_iters, dst_base, src_of_dst, dst_iters, n_surv;
+    int ext_cap = 0;
     // staging for the host-buffer entry points (grown on demand, never beyond max_frames)
     DevBuf in_a, in_b, out_a, sigma;
     // transmitter / monitor (allocated on first use)
@@ -229,6 +232,57 @@ demap_args(dvbs2_cuda_handle* h, const float* d_sigma, const float* d_sym, int n
     return d;
 }
 
+// LDPC decode of slots [first_frame, first_frame + n_frames): one round, or two rounds with frame compaction in between
+int
+run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frames, int8_t* d_cwd, int32_t* d_nit)
+{
+    LdpcLaunch a = ldpc_args(h, s, first_frame, n_frames, d_cwd, d_nit);
+    const int gsz = 32 * h->nf;
+    const bool two_rounds = h->ext_cap > 0 && h->cfg.early_stop && h->cfg.n_ite >= 4 && a.n_groups >= 2;
+    if (!two_rounds)
+    {
+        CU(h, launch_ldpc_decode(a, h->cfg.precision, s));
+        h->launches += 1;
+        return DVBS2_OK;
+    }
+    int slot = 0;
+    for (int i = 0; i < N_PIPE; i++)
+        if (s == h->pipe[i]) slot = 1 + i;
+    // round 1: a group hands its live frames over once fewer than half of its frames are still iterating
+    a.exit_below = gsz / 2;
+    a.surv_mask = (uint32_t*)h->surv_mask.p + first_frame / 32;
+    a.surv_iters = (int*)h->surv_iters.p + first_frame;
+    CU(h, launch_ldpc_decode(a, h->cfg.precision, s));
+    // survivors -> dense groups in the extension region (each group exports < gsz/2 frames, so < n_frames/2 in total)
+    const size_t ext0 = (size_t)h->max_frames + first_frame / 2; // multiple of gsz: first_frame is a multiple of 256
+    const int e0 = first_frame / 2;
+    const int cap = std::min(h->ext_cap - e0, (a.n_groups * (gsz / 2) + gsz - 1) / gsz * gsz);
+    CompactLaunch c{};
+    c.surv_mask = a.surv_mask, c.surv_iters = a.surv_iters;
+    c.dst_base = (int*)h->dst_base.p + first_frame / gsz;
+    c.n_surv = (int*)h->n_surv.p + slot;
+    c.src_of_dst = (int*)h->src_of_dst.p + e0, c.dst_iters = (int*)h->dst_iters.p + e0;
+    c.var_src = a.var, c.var_dst = (char*)h->var.p + ext0 * N_LDPC * h->elt;
+    c.cn_src = a.cn, c.cn_dst = (uint4*)h->cn.p + ext0 * h->mc.M;
+    c.out_hd_src = a.out_hd, c.out_hd_dst = (uint32_t*)h->out_hd.p + (ext0 / 32) * N_LDPC;
+    c.n_groups = a.n_groups, c.nf = h->nf, c.cap = cap, c.M = h->mc.M;
+    c.nf_dst = ldpc_round2_frames_per_lane(h->cfg.precision);
+    CU(h, launch_compact(c, h->cfg.precision, s));
+    // round 2: the survivors, to the end of their iteration budget
+    LdpcLaunch b = a;
+    b.var = c.var_dst, b.cn = c.cn_dst;
+    b.hd = (uint32_t*)h->hd.p + (ext0 / 32) * N_LDPC;
+    b.out_hd = (uint32_t*)h->out_hd.p + (ext0 / 32) * N_LDPC;
+    b.queue = h->d_queue + 8 + slot;
+    b.n_frames = cap, b.n_groups = cap / (32 * c.nf_dst), b.nf = c.nf_dst;
+    b.n_slots_dev = c.n_surv, b.slot_frame = c.src_of_dst, b.slot_iters = c.dst_iters;
+    b.surv_mask = nullptr, b.surv_iters = nullptr, b.exit_below = 0;
+    CU(h, launch_ldpc_decode(b, h->cfg.precision, s));
+    CU(h, launch_merge_back(c, s));
+    h->launches += 6;
+    return DVBS2_OK;
+}
+
 // device-side pieces, all asynchronous on `s`; frames occupy device slots [first_frame, ...), first_frame a multiple of the group size
 int
 run_ldpc(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const void* d_Y, int8_t* d_cwd, int32_t* d_VK,
@@ -239,11 +293,11 @@ run_ldpc(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const void* d_Y,
     TRY(prof_mark(h, s, P_PACK));
     CU(h, launch_pack_llr(d_Y, var, h->cfg.precision, n_frames, s));
     TRY(prof_mark(h, s, P_LDPC));
-    CU(h, launch_ldpc_decode(ldpc_args(h, s, first_frame, n_frames, d_cwd, d_nit), h->cfg.precision, s));
+    TRY(run_ldpc_core(h, s, first_frame, n_frames, d_cwd, d_nit));
     TRY(prof_mark(h, s, P_UNPACK));
     CU(h, launch_unpack_bits((uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC, d_VK, N_LDPC, h->mc.N_bch, n_frames, s));
     TRY(prof_mark(h, s, P_END));
-    h->launches += 3;
+    h->launches += 2;
     return DVBS2_OK;
 }
 
@@ -273,13 +327,13 @@ run_chain(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const float* d_
     TRY(prof_mark(h, s, P_DEMAP));
     CU(h, launch_demap_to_var(demap_args(h, d_sigma, d_sym, n_frames), var, h->cfg.precision, h->nf, s));
     TRY(prof_mark(h, s, P_LDPC));
-    CU(h, launch_ldpc_decode(ldpc_args(h, s, first_frame, n_frames, d_cwd_ldpc, d_nit), h->cfg.precision, s));
+    TRY(run_ldpc_core(h, s, first_frame, n_frames, d_cwd_ldpc, d_nit));
     TRY(prof_mark(h, s, P_BCH));
     CU(h, launch_bch_decode(bch_args(h, first_frame, n_frames, d_cwd_bch), h->bch, s));
     TRY(prof_mark(h, s, P_UNPACK));
     CU(h, launch_unpack_bits((uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC, d_VK, N_LDPC, h->mc.K_bch, n_frames, s));
     TRY(prof_mark(h, s, P_END));
-    h->launches += 5;
+    h->launches += 4;
     return DVBS2_OK;
 }
 
@@ -389,7 +443,8 @@ extern "C"
         if (!h) return DVBS2_OK;
         cudaSetDevice(h->cfg.device);
         for (DevBuf* b : { &h->var, &h->cn, &h->hd, &h->out_hd, &h->rem, &h->nz, &h->cwd_ldpc, &h->cwd_bch, &h->nit,
-                           &h->stats, &h->in_a, &h->in_b, &h->out_a, &h->sigma, &h->tx_src, &h->tx_cw, &h->tx_scr,
+                           &h->stats, &h->surv_mask, &h->surv_iters, &h->dst_base, &h->src_of_dst, &h->dst_iters, &h->n_surv,
+                           &h->in_a, &h->in_b, &h->out_a, &h->sigma, &h->tx_src, &h->tx_cw, &h->tx_scr,
                            &h->tx_gmask, &h->mon })
             if (b->p) cudaFree(b->p);
         for (void* p : { (void*)h->d_idx, (void*)h->d_idx32, (void*)h->d_last, (void*)h->d_queue, (void*)h->d_alpha_to,
@@ -494,9 +549,15 @@ extern "C"
         memcpy(h->bch.synd_mat, bt.synd_mat, sizeof(bt.synd_mat));
 
         const size_t G = (size_t)h->max_groups, F = (size_t)h->max_frames;
+        const int gsz = 32 * h->nf;
+        h->ext_cap = cfg->no_compaction ? 0 : (h->max_frames / 2 + gsz - 1) / gsz * gsz + gsz;
+        const size_t FE = F + h->ext_cap, GE = FE / 32; // slots incl. the compaction region
         int rc;
-        if ((rc = ensure(h, h->var, G * N_LDPC * 32 * h->elt)) || (rc = ensure(h, h->cn, G * mc.M * 32 * sizeof(uint4))) ||
-            (rc = ensure(h, h->hd, G * N_LDPC * 4)) || (rc = ensure(h, h->out_hd, G * N_LDPC * 4)) ||
+        if ((rc = ensure(h, h->var, FE * N_LDPC * h->elt)) || (rc = ensure(h, h->cn, FE * mc.M * sizeof(uint4))) ||
+            (rc = ensure(h, h->hd, GE * N_LDPC * 4)) || (rc = ensure(h, h->out_hd, GE * N_LDPC * 4)) ||
+            (rc = ensure(h, h->surv_mask, G * 4 + 4)) || (rc = ensure(h, h->surv_iters, F * 4 + 4)) ||
+            (rc = ensure(h, h->dst_base, G * 4 + 4)) || (rc = ensure(h, h->src_of_dst, (size_t)h->ext_cap * 4 + 4)) ||
+            (rc = ensure(h, h->dst_iters, (size_t)h->ext_cap * 4 + 4)) || (rc = ensure(h, h->n_surv, 8 * sizeof(int))) ||
             (rc = ensure(h, h->rem, G * BCH_NPOLY * GF_M * 4)) || (rc = ensure(h, h->nz, G * 4)) ||
             (rc = ensure(h, h->cwd_ldpc, F)) || (rc = ensure(h, h->cwd_bch, F)) || (rc = ensure(h, h->nit, F * 4)) ||
             (rc = ensure(h, h->stats, STAT_COUNT * sizeof(unsigned long long))))

@@ -7,7 +7,7 @@
 
 namespace dvbs2
 {
-constexpr int LDPC_WARPS_PER_BLOCK = 8;
+constexpr int LDPC_WARPS = 12; // warps of the persistent LDPC CTA (one CTA per SM)
 
 enum StatSlot
 {
@@ -24,7 +24,7 @@ enum StatSlot
 //   var    [groups][16200][32][NF]   R      variable-node values (LLR + messages); element (lane l, j) = frame
 //                                            (group*NF + j)*32 + l
 //   cn     [groups][M][NF][32]       uint4  compressed check state {out1, out2, sign bits, eq bits}
-//   hd     [subgroups][16200]        u32    running hard decisions
+//   hd     [groups][16200][NF]       u32    running hard decisions (the NF subgroup words of a variable are adjacent)
 //   out_hd [subgroups][16200]        u32    hard decisions snapshotted when each frame stopped iterating
 struct LdpcLaunch
 {
@@ -45,7 +45,39 @@ struct LdpcLaunch
     int k8; // norm * 8 if that is an integer in 1..8, else 0
     int early_stop;
     int n_sms;
+    // two-round decoding (frame compaction): all null / 0 for a plain single-round launch
+    const int* n_slots_dev;  // round 2: number of occupied slots, known only on the device (n_frames = capacity)
+    const int* slot_frame;   // round 2: [slots] frame index (for cwd / n_iter) of each slot
+    const int* slot_iters;   // round 2: [slots] iterations already spent; such frames carry check state
+    uint32_t* surv_mask;     // round 1: [subgroups] lanes handed over to round 2 (0 if none)
+    int* surv_iters;         // round 1: [slots] iterations spent by the lanes handed over
+    int exit_below;          // round 1: hand the group's live frames over once fewer than this many remain (0 = never)
+    int nf;                  // frames per lane of this launch (0 = ldpc_frames_per_lane(precision))
 };
+
+// Frame compaction between the two rounds: survivors of round 1 (src slots) are packed, in slot order, into dense groups
+// of fresh slots (dst), their var / check state copied; after round 2 their hard decisions return to the src subgroups.
+struct CompactLaunch
+{
+    const uint32_t* surv_mask; // [n_groups * nf]
+    const int* surv_iters;     // [n_groups * nf * 32]
+    int* dst_base;             // [n_groups]   exclusive prefix of survivors per group
+    int* n_surv;               // [1]
+    int* src_of_dst;           // [cap]        source slot of each destination slot (= frame index for the outputs)
+    int* dst_iters;            // [cap]
+    const void* var_src;
+    void* var_dst;
+    const uint4* cn_src;
+    uint4* cn_dst;
+    uint32_t* out_hd_src;      // [n_groups * nf][16200]  round-1 slots (merge target)
+    const uint32_t* out_hd_dst; // [cap / 32][16200]
+    int n_groups, nf, cap, M;
+    int nf_dst;                // frames per lane of the destination groups (round 2 may use narrower groups: its few
+                               // warps are latency-bound, so halving the work per check halves its duration)
+};
+int ldpc_round2_frames_per_lane(int precision); // 1 (f32), else as round 1
+cudaError_t launch_compact(const CompactLaunch& c, int precision, cudaStream_t s);    // scan + expand + copy (3 kernels)
+cudaError_t launch_merge_back(const CompactLaunch& c, cudaStream_t s);
 
 int ldpc_frames_per_lane(int precision); // NF: 2 (f32, i16), 4 (i8)
 cudaError_t launch_ldpc_decode(const LdpcLaunch& a, int precision, cudaStream_t s);

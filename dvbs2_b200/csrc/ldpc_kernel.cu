@@ -58,6 +58,9 @@ struct Arith<float>
     __device__ static C vmax(C a, C b) { return fmaxf(a, b); }
     __device__ static C normalize(C v, float f, int) { return __fmul_rn(v, f); } // Update_rule_NMS.hxx:41-46
     __device__ static C with_sign(C m, unsigned s) { return __uint_as_float(__float_as_uint(m) | (s << 31)); }
+    __device__ static unsigned raw(C t) { return __float_as_uint(t); } // bit 31 = neg(t)
+    // magnitude m >= 0 with the sign held in bit 31 of w
+    __device__ static C apply_sign(C m, unsigned w) { return __uint_as_float(__float_as_uint(m) | (w & 0x80000000u)); }
     __device__ static unsigned pack(C a, C b, unsigned& hi)
     {
         hi = __float_as_uint(b);
@@ -96,6 +99,8 @@ struct ArithInt
         return wrap(r);
     }
     __device__ static C with_sign(C m, unsigned s) { return wrap(s ? -m : m); }
+    __device__ static unsigned raw(C t) { return (unsigned)t; } // bit 31 = neg(t): values are sign-extended ints
+    __device__ static C apply_sign(C m, unsigned w) { return wrap((int)w < 0 ? -m : m); }
     __device__ static unsigned pack(C a, C b, unsigned& hi)
     {
         hi = 0;
@@ -147,7 +152,7 @@ struct CheckRegs
 };
 
 template<typename R, int DI, int NF>
-__global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kernel(const LdpcLaunch a)
+__global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const LdpcLaunch a)
 {
     using A = Arith<R>;
     using C = typename A::C;
@@ -155,7 +160,8 @@ __global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kern
     constexpr int NW = sizeof(Raw) / 4;  // 32-bit words per raw vector
     constexpr int D = DI + 2;            // edges per check incl. the two parity edges (bit DI = in, DI+1 = out)
     constexpr int IW = (DI + 1) / 2;     // u32 words per index row
-    constexpr size_t VSTRIDE = 32 * NF;  // elements of R between consecutive variables
+    constexpr unsigned VB = 32 * NF * sizeof(R); // bytes between consecutive variables of a group
+    using HdVec = typename RawVec<4 * NF>::T;    // the NF hard-decision words of one variable
 
     extern __shared__ uint32_t smem[];
     const int K = a.K, M = a.M;
@@ -169,17 +175,25 @@ __global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kern
 
     const int lane = threadIdx.x & 31;
 
+    // slots of this launch: round 1 decodes frames in place (slot = frame); round 2 decodes the survivors that the
+    // compaction step packed into fresh slots, their count known only on the device
+    const int n_slots = a.n_slots_dev ? min(*a.n_slots_dev, a.n_frames) : a.n_frames;
+    const int n_groups = (n_slots + 32 * NF - 1) / (32 * NF);
+    const bool resumed = a.slot_iters != nullptr; // resumed frames carry check state from their first round
+
     for (;;)
     {
         int g = 0;
         if (lane == 0) g = atomicAdd(a.queue, 1);
         g = __shfl_sync(FULL, g, 0);
-        if (g >= a.n_groups) break;
+        if (g >= n_groups) break;
 
-        R* __restrict__ var = (R*)a.var + (size_t)g * N_LDPC * VSTRIDE + lane * NF;
+        // byte offsets inside a group fit 32 bits: (warp-uniform base) + variable * VB + lane offset
+        char* __restrict__ vbytes = (char*)a.var + (size_t)g * N_LDPC * VB;
+        const unsigned loff = lane * NF * (unsigned)sizeof(R);
         uint4* __restrict__ cn = a.cn + (size_t)g * M * NF * 32 + lane;
-        uint32_t* __restrict__ hd = a.hd + (size_t)g * NF * N_LDPC;
-        uint32_t* __restrict__ out_hd = a.out_hd + (size_t)g * NF * N_LDPC;
+        uint32_t* __restrict__ hd = a.hd + (size_t)g * NF * N_LDPC;       // running hard decisions, [v][NF] words
+        uint32_t* __restrict__ out_hd = a.out_hd + (size_t)g * NF * N_LDPC; // final ones, [NF][v] (subgroup-major)
 
         unsigned active[NF], done[NF], failed[NF];
         int my_iters[NF];
@@ -187,14 +201,15 @@ __global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kern
 #pragma unroll
         for (int j = 0; j < NF; j++)
         {
-            const int frame = (g * NF + j) * 32 + lane;
-            active[j] = __ballot_sync(FULL, frame < a.n_frames);
+            const int slot = (g * NF + j) * 32 + lane;
+            active[j] = __ballot_sync(FULL, slot < n_slots);
             done[j] = failed[j] = 0;
-            my_iters[j] = 0;
+            my_iters[j] = (resumed && slot < n_slots) ? a.slot_iters[slot] : 0;
             any_active |= active[j] != 0;
         }
+        bool exported = false;
 
-        for (int ite = 0; ite < a.n_ite && any_active; ite++)
+        for (int ite = 0; any_active; ite++)
         {
             bool mine[NF];
 #pragma unroll
@@ -209,6 +224,7 @@ __global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kern
 #pragma unroll
             for (int j = 0; j < NF; j++)
                 chain[j] = A::max_value();
+            const bool have_state = resumed || ite > 0;
 
             // ---- requests everything check c reads from HBM (hazard-free ahead of time, see header)
             auto issue = [&](CheckRegs<R, DI, NF>& r, int c) {
@@ -217,16 +233,22 @@ __global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kern
                 for (int i = 0; i < DI; i++)
                 {
                     const unsigned vi = (row[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-                    r.v[i] = __ldcg(reinterpret_cast<const Raw*>(var + (size_t)vi * VSTRIDE));
+                    r.v[i] = __ldcg(reinterpret_cast<const Raw*>(vbytes + (vi * VB + loff)));
                 }
-                r.v[DI] = __ldcg(reinterpret_cast<const Raw*>(var + (size_t)(K + c) * VSTRIDE));
+                r.v[DI] = __ldcg(reinterpret_cast<const Raw*>(vbytes + ((unsigned)(K + c) * VB + loff)));
 #pragma unroll
                 for (int j = 0; j < NF; j++)
-                    r.st[j] = ite > 0 ? __ldcg(cn + (size_t)(c * NF + j) * 32) : make_uint4(0u, 0u, 0u, 0u);
+                    r.st[j] = have_state ? __ldcg(cn + (size_t)(c * NF + j) * 32) : make_uint4(0u, 0u, 0u, 0u);
             };
 
-            // ---- check c on the values in r (Update_rule_MS.hxx:57-92, Update_rule_NMS.hxx:100-106, ...layered.hxx:198-203)
-            auto compute = [&](CheckRegs<R, DI, NF>& r, int c) {
+            // One register set: pass 1 turns the loaded values into t = var - msg (Update_rule_MS.hxx:57-67), which frees
+            // them for the loads of check c+1; those are in flight during pass 2 (new messages, stores; :82-92 and
+            // ...layered.hxx:198-203).  Sign and "== min1" bits of edge i live at bit D-1-i of the state words.
+            CheckRegs<R, DI, NF> r;
+            issue(r, 0);
+#pragma unroll 1
+            for (int c = 0; c < M; c++)
+            {
                 const uint32_t* row = s_idx + c * IW;
                 const uint32_t lastm = s_last[c];
                 C t[D][NF];
@@ -244,33 +266,32 @@ __global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kern
                     for (int i = 0; i < D; i++)
                     {
                         C v;
-                        if (i < DI)
-                        {
-                            uint32_t w[NW];
-                            memcpy(w, &r.v[i], sizeof(Raw));
-                            v = A::from_raw(w, j);
-                        }
-                        else if (i == DI)
+                        if (i == DI)
                             v = chain[j];
                         else
                         {
                             uint32_t w[NW];
-                            memcpy(w, &r.v[DI], sizeof(Raw));
+                            memcpy(w, &r.v[i < DI ? i : DI], sizeof(Raw));
                             v = A::from_raw(w, j);
                         }
-                        const C m = A::with_sign(((oeq >> i) & 1u) ? o1 : o2, (osg >> i) & 1u);
-                        C ti = A::sub(v, m);
+                        constexpr int dummy = 0;
+                        (void)dummy;
+                        const int b = D - 1 - i;
+                        const C mag = (oeq & (1u << b)) ? o1 : o2;
+                        C ti = A::sub(v, A::apply_sign(mag, osg << (31 - b)));
                         if (i == DI && c == 0) ti = A::max_value(); // check 0 has no incoming chain edge
                         t[i][j] = ti;
                         const C ab = A::absv(ti);
-                        sa ^= A::neg(ti);
+                        sa ^= A::raw(ti);
                         m2 = A::vmin(m2, A::vmax(ab, m1));
                         m1 = A::vmin(m1, ab);
                     }
                     min1[j] = m1, sacc[j] = sa;
-                    c1[j] = A::vmax((C)0, A::normalize(m2, a.norm, a.k8));
+                    c1[j] = A::vmax((C)0, A::normalize(m2, a.norm, a.k8)); // Update_rule_NMS.hxx:100-106
                     c2[j] = A::vmax((C)0, A::normalize(m1, a.norm, a.k8));
                 }
+
+                if (c + 1 < M) issue(r, c + 1);
 
                 unsigned nsg[NF], neq[NF];
 #pragma unroll
@@ -284,13 +305,13 @@ __global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kern
                     for (int j = 0; j < NF; j++)
                     {
                         const C ti = t[i][j];
-                        const unsigned e = (A::absv(ti) == min1[j]);
-                        const unsigned s = sacc[j] ^ A::neg(ti);
-                        nv[j] = A::add(ti, A::with_sign(e ? c1[j] : c2[j], s));
-                        neq[j] |= e << i;
-                        nsg[j] |= s << i;
+                        const bool e = A::absv(ti) == min1[j];
+                        const unsigned x = sacc[j] ^ A::raw(ti); // bit 31: sign of the new message
+                        nv[j] = A::add(ti, A::apply_sign(e ? c1[j] : c2[j], x));
+                        if (e) neq[j] |= 1u << (D - 1 - i);
+                        nsg[j] = __funnelshift_l(x, nsg[j], 1);
                     }
-                    int vi;
+                    unsigned vi;
                     bool ballot;
                     if (i < DI)
                     {
@@ -320,15 +341,16 @@ __global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kern
                             A::to_raw(w, j, nv[j]);
                         Raw out;
                         memcpy(&out, w, sizeof(Raw));
-                        __stcg(reinterpret_cast<Raw*>(var + (size_t)vi * VSTRIDE), out);
+                        __stcg(reinterpret_cast<Raw*>(vbytes + (vi * VB + loff)), out);
                     }
-                    // the vote is unconditional (no divergence scaffolding around it); only the store is predicated
+                    // the votes are unconditional (no divergence scaffolding around them); one predicated NF-word store
+                    HdVec hw;
+                    uint32_t hww[NF];
 #pragma unroll
                     for (int j = 0; j < NF; j++)
-                    {
-                        const unsigned w = __ballot_sync(FULL, A::lt0(nv[j]));
-                        if (ballot && lane == 0) __stcg(hd + (size_t)j * N_LDPC + vi, w);
-                    }
+                        hww[j] = __ballot_sync(FULL, A::lt0(nv[j]));
+                    memcpy(&hw, hww, sizeof(HdVec));
+                    if (ballot && lane == 0) __stcg(reinterpret_cast<HdVec*>(hd + (size_t)vi * NF), hw);
                 }
 #pragma unroll
                 for (int j = 0; j < NF; j++)
@@ -338,18 +360,6 @@ __global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kern
                         const unsigned lo = A::pack(c1[j], c2[j], hi);
                         __stcg(cn + (size_t)(c * NF + j) * 32, make_uint4(lo, hi, nsg[j], neq[j]));
                     }
-            };
-
-            // one loop body (~27 KB of SASS, inside the 32 KB L1.5 instruction cache; the two-body ping-pong version was
-            // 52 KB and stalled on instruction fetch): rb receives check c+1 while check c is computed from ra
-            CheckRegs<R, DI, NF> ra, rb;
-            issue(ra, 0);
-#pragma unroll 1
-            for (int c = 0; c < M; c++)
-            {
-                if (c + 1 < M) issue(rb, c + 1);
-                compute(ra, c);
-                ra = rb;
             }
 #pragma unroll
             for (int j = 0; j < NF; j++)
@@ -364,35 +374,43 @@ __global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kern
             for (int c = lane; c < M; c += 32)
             {
                 const uint32_t* row = s_idx + c * IW;
+                uint32_t p[NF];
+                auto fold = [&](unsigned v) {
+                    const HdVec h = __ldcg(reinterpret_cast<const HdVec*>(hd + (size_t)v * NF));
+                    uint32_t w[NF];
+                    memcpy(w, &h, sizeof(HdVec));
+#pragma unroll
+                    for (int j = 0; j < NF; j++)
+                        p[j] ^= w[j];
+                };
 #pragma unroll
                 for (int j = 0; j < NF; j++)
-                {
-                    const uint32_t* hj = hd + (size_t)j * N_LDPC;
-                    unsigned p = __ldcg(hj + K + c);
-                    if (c > 0) p ^= __ldcg(hj + K + c - 1);
+                    p[j] = 0;
+                fold(K + c);
+                if (c > 0) fold(K + c - 1);
 #pragma unroll
-                    for (int i = 0; i < DI; i++)
-                        p ^= __ldcg(hj + ((row[i >> 1] >> ((i & 1) * 16)) & 0xffffu));
-                    unsat[j] |= p;
-                }
+                for (int i = 0; i < DI; i++)
+                    fold((row[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+#pragma unroll
+                for (int j = 0; j < NF; j++)
+                    unsat[j] |= p[j];
             }
-            const bool last = (ite == a.n_ite - 1);
             any_active = false;
+            int n_active = 0;
 #pragma unroll
             for (int j = 0; j < NF; j++)
             {
                 unsat[j] = __reduce_or_sync(FULL, unsat[j]);
-                unsigned fin = active[j] & ~unsat[j];
-                if (!a.early_stop) fin = 0;
-                if (last) fin = active[j];
+                const unsigned spent = __ballot_sync(FULL, mine[j] && my_iters[j] >= a.n_ite); // iteration budget used up
+                unsigned fin = a.early_stop ? (active[j] & ~unsat[j]) : 0u;
+                fin |= spent;
                 if (fin)
                 {
                     // snapshot the finishing lanes' hard decisions
-                    const uint32_t* hj = hd + (size_t)j * N_LDPC;
                     uint32_t* oj = out_hd + (size_t)j * N_LDPC;
                     for (int v = lane; v < N_LDPC; v += 32)
                     {
-                        const unsigned w = __ldcg(hj + v);
+                        const unsigned w = __ldcg(hd + (size_t)v * NF + j);
                         const unsigned o = done[j] ? __ldcg(oj + v) : 0u;
                         __stcg(oj + v, (o & done[j]) | (w & fin));
                     }
@@ -401,26 +419,46 @@ __global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kern
                     active[j] &= ~fin;
                 }
                 any_active |= active[j] != 0;
+                n_active += __popc(active[j]);
             }
             __syncwarp();
+            // ---- hand the stragglers over to the compaction step once most of the group has converged: they continue in
+            //      a dense group instead of keeping this warp (and its 256-byte chunks) busy for a few live lanes
+            if (a.exit_below > 0 && n_active > 0 && n_active < a.exit_below && a.n_ite - (ite + 1) >= 2)
+            {
+                exported = true;
+                break;
+            }
+        }
+
+        // survivors of this group (none unless exported): mask per subgroup + iterations already spent per slot
+        if (a.surv_mask)
+        {
+#pragma unroll
+            for (int j = 0; j < NF; j++)
+            {
+                const unsigned m = exported ? active[j] : 0u;
+                if (lane == 0) a.surv_mask[g * NF + j] = m;
+                if ((m >> lane) & 1) a.surv_iters[(g * NF + j) * 32 + lane] = my_iters[j];
+            }
         }
 
         int it_sum = 0, n_valid = 0, n_failed = 0;
 #pragma unroll
         for (int j = 0; j < NF; j++)
         {
-            const int frame = (g * NF + j) * 32 + lane;
-            const bool valid = frame < a.n_frames;
-            if (valid)
+            const int slot = (g * NF + j) * 32 + lane;
+            const bool fin = (done[j] >> lane) & 1;
+            if (fin)
             {
+                const int frame = a.slot_frame ? a.slot_frame[slot] : slot;
                 const bool ok = !((failed[j] >> lane) & 1);
                 if (a.cwd) a.cwd[frame] = (int8_t)ok;
                 if (a.n_iter) a.n_iter[frame] = my_iters[j];
             }
-            const unsigned vm = __ballot_sync(FULL, valid);
-            it_sum += __reduce_add_sync(FULL, valid ? my_iters[j] : 0);
-            n_valid += __popc(vm);
-            n_failed += __popc(failed[j] & vm);
+            it_sum += __reduce_add_sync(FULL, fin ? my_iters[j] : 0);
+            n_valid += __popc(done[j]);
+            n_failed += __popc(failed[j] & done[j]);
         }
         if (lane == 0 && a.stats)
         {
@@ -428,6 +466,147 @@ __global__ void __launch_bounds__(LDPC_WARPS_PER_BLOCK * 32, 1) ldpc_decode_kern
             atomicAdd(a.stats + STAT_LDPC_ITERS, (unsigned long long)it_sum);
             atomicAdd(a.stats + STAT_LDPC_FAIL, (unsigned long long)n_failed);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- frame compaction
+// survivors per group -> exclusive prefix (one block; groups are few thousand)
+__global__ void __launch_bounds__(1024) compact_scan_kernel(const CompactLaunch c)
+{
+    __shared__ int part[1024];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int g0 = 0; g0 < c.n_groups; g0 += 1024)
+    {
+        const int g = g0 + threadIdx.x;
+        int n = 0;
+        if (g < c.n_groups)
+            for (int j = 0; j < c.nf; j++)
+                n += __popc(c.surv_mask[g * c.nf + j]);
+        part[threadIdx.x] = n;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) // Hillis-Steele inclusive scan
+        {
+            const int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+            __syncthreads();
+            part[threadIdx.x] += v;
+            __syncthreads();
+        }
+        if (g < c.n_groups) c.dst_base[g] = carry + part[threadIdx.x] - n;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += part[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *c.n_surv = min(carry, c.cap);
+}
+
+// one thread per source subgroup: destination slots of its survivors, in slot order
+__global__ void
+compact_expand_kernel(const CompactLaunch c)
+{
+    const int sg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sg >= c.n_groups * c.nf) return;
+    const int g = sg / c.nf, j = sg % c.nf;
+    int d = c.dst_base[g];
+    for (int k = 0; k < j; k++)
+        d += __popc(c.surv_mask[g * c.nf + k]);
+    unsigned m = c.surv_mask[sg];
+    while (m)
+    {
+        const int l = __ffs(m) - 1;
+        m &= m - 1;
+        if (d < c.cap)
+        {
+            c.src_of_dst[d] = sg * 32 + l;
+            c.dst_iters[d] = c.surv_iters[sg * 32 + l];
+        }
+        d++;
+    }
+}
+
+// warp = (destination group, part): gathers the state of its 32*NF survivors.  Survivors of one source group are
+// neighbours in destination order, so the scattered element loads of a warp fall into a handful of source chunks.
+constexpr int COMPACT_PARTS = 8;
+template<typename R, int NF, int ND> // NF: frames per lane of the source groups, ND: of the destination groups
+__global__ void __launch_bounds__(128) compact_copy_kernel(const CompactLaunch c)
+{
+    const int lane = threadIdx.x & 31;
+    const int d = blockIdx.x;
+    const int part = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int n_surv = *c.n_surv;
+    if (d * 32 * ND >= n_surv || part >= COMPACT_PARTS) return;
+    size_t vbase[ND], cbase[ND];
+    bool valid[ND];
+#pragma unroll
+    for (int j = 0; j < ND; j++)
+    {
+        const int ds = (d * ND + j) * 32 + lane;
+        valid[j] = ds < n_surv;
+        const int s = valid[j] ? c.src_of_dst[ds] : 0;
+        const int gs = s / (32 * NF), js = (s / 32) % NF, ls = s % 32;
+        vbase[j] = ((size_t)gs * N_LDPC * 32 + ls) * NF + js;
+        cbase[j] = ((size_t)gs * c.M * NF + js) * 32 + ls;
+    }
+    const R* vs = (const R*)c.var_src;
+    R* vd = (R*)c.var_dst + ((size_t)d * N_LDPC * 32 + lane) * ND;
+    const int v0 = (int)((long)N_LDPC * part / COMPACT_PARTS), v1 = (int)((long)N_LDPC * (part + 1) / COMPACT_PARTS);
+#pragma unroll 4
+    for (int v = v0; v < v1; v++)
+    {
+        R x[ND];
+#pragma unroll
+        for (int j = 0; j < ND; j++)
+            x[j] = valid[j] ? __ldcg(vs + vbase[j] + (size_t)v * 32 * NF) : (R)0;
+#pragma unroll
+        for (int j = 0; j < ND; j++)
+            vd[(size_t)v * 32 * ND + j] = x[j];
+    }
+    uint4* cd = c.cn_dst + (size_t)d * c.M * ND * 32 + lane;
+    const int c0 = (int)((long)c.M * part / COMPACT_PARTS), c1 = (int)((long)c.M * (part + 1) / COMPACT_PARTS);
+#pragma unroll 2
+    for (int k = c0; k < c1; k++)
+#pragma unroll
+        for (int j = 0; j < ND; j++)
+            cd[(size_t)(k * ND + j) * 32] = valid[j] ? __ldcg(c.cn_src + cbase[j] + (size_t)k * NF * 32) : make_uint4(0u, 0u, 0u, 0u);
+}
+
+// after round 2: the survivors' final hard decisions go back to the bit lanes of their round-1 subgroups.
+// warp = (source group, part), lanes = consecutive variables.
+__global__ void __launch_bounds__(128) merge_back_kernel(const CompactLaunch c)
+{
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x;
+    const int part = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (part >= COMPACT_PARTS) return;
+    int d0 = c.dst_base[g];
+    const int v0 = (int)((long)N_LDPC * part / COMPACT_PARTS), v1 = (int)((long)N_LDPC * (part + 1) / COMPACT_PARTS);
+    for (int j = 0; j < c.nf; j++)
+    {
+        const unsigned m = c.surv_mask[g * c.nf + j];
+        if (m)
+        {
+            uint32_t* dst = c.out_hd_src + (size_t)(g * c.nf + j) * N_LDPC;
+            for (int v = v0 + lane; v < v1; v += 32)
+            {
+                uint32_t w = dst[v];
+                unsigned mm = m;
+                int d = d0;
+                while (mm)
+                {
+                    const int l = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    if (d < c.cap)
+                    {
+                        const uint32_t bit = (c.out_hd_dst[(size_t)(d >> 5) * N_LDPC + v] >> (d & 31)) & 1u;
+                        w = (w & ~(1u << l)) | (bit << l);
+                    }
+                    d++;
+                }
+                dst[v] = w;
+            }
+        }
+        d0 += __popc(m);
     }
 }
 
@@ -509,9 +688,11 @@ launch_ldpc_k(const LdpcLaunch& a, cudaStream_t s)
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(a.queue, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
-    const int want = (a.n_groups + LDPC_WARPS_PER_BLOCK - 1) / LDPC_WARPS_PER_BLOCK;
-    const int blocks = want < a.n_sms ? want : a.n_sms;
-    k<<<blocks, LDPC_WARPS_PER_BLOCK * 32, smem, s>>>(a);
+    const int groups = (a.n_frames + 32 * NF - 1) / (32 * NF); // capacity when the real count is on the device
+    // spread the groups over all SMs (a warp's walk through the checks is latency-bound, so 4 warps on each of 148 SMs
+    // finish sooner than 12 warps on each of 50); the queue hands groups to whichever warp is free
+    const int blocks = groups < a.n_sms ? groups : a.n_sms;
+    k<<<blocks, LDPC_WARPS * 32, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -529,11 +710,49 @@ launch_ldpc_decode(const LdpcLaunch& a, int precision, cudaStream_t s)
 {
     switch (precision)
     {
-        case 0: return launch_ldpc_t<float, 2>(a, s);
+        case 0: return a.nf == 1 ? launch_ldpc_t<float, 1>(a, s) : launch_ldpc_t<float, 2>(a, s);
         case 1: return launch_ldpc_t<int16_t, 2>(a, s);
         case 2: return launch_ldpc_t<int8_t, 4>(a, s);
     }
     return cudaErrorInvalidValue;
+}
+
+template<typename R, int NF, int ND>
+static cudaError_t
+launch_compact_t(const CompactLaunch& c, cudaStream_t s)
+{
+    compact_scan_kernel<<<1, 1024, 0, s>>>(c);
+    compact_expand_kernel<<<(c.n_groups * c.nf + 127) / 128, 128, 0, s>>>(c);
+    const dim3 grid(c.cap / (32 * ND), (COMPACT_PARTS + 3) / 4);
+    if (grid.x > 0) compact_copy_kernel<R, NF, ND><<<grid, 128, 0, s>>>(c);
+    return cudaGetLastError();
+}
+
+int
+ldpc_round2_frames_per_lane(int precision)
+{
+    return precision == 0 ? 1 : ldpc_frames_per_lane(precision);
+}
+
+cudaError_t
+launch_compact(const CompactLaunch& c, int precision, cudaStream_t s)
+{
+    if (c.nf != ldpc_frames_per_lane(precision) || c.nf_dst != ldpc_round2_frames_per_lane(precision)) return cudaErrorInvalidValue;
+    switch (precision)
+    {
+        case 0: return launch_compact_t<float, 2, 1>(c, s);
+        case 1: return launch_compact_t<int16_t, 2, 2>(c, s);
+        case 2: return launch_compact_t<int8_t, 4, 4>(c, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t
+launch_merge_back(const CompactLaunch& c, cudaStream_t s)
+{
+    const dim3 grid(c.n_groups, (COMPACT_PARTS + 3) / 4);
+    merge_back_kernel<<<grid, 128, 0, s>>>(c);
+    return cudaGetLastError();
 }
 
 cudaError_t

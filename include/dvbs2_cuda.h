@@ -75,7 +75,10 @@ extern "C"
         int device;      /* CUDA device ordinal                                                            */
         int quant_bits;  /* Quantizer_pow2 saturation_pos (AFF3CT default 6), used by int precisions       */
         int quant_dec;   /* Quantizer_pow2 fixed_point_pos (AFF3CT default 2)                              */
-        int reserved[7]; /* must be 0                                                                      */
+        int no_compaction; /* 0 (default): frames still iterating when most of their 64-frame group has converged are
+                              packed into dense groups for the remaining iterations (same results, fewer bytes);
+                              1: every frame stays in its group                                                  */
+        int reserved[6]; /* must be 0                                                                      */
     } dvbs2_cuda_cfg;
 
     typedef struct

@@ -15,11 +15,12 @@ def _llrs(oracle, modcod, F, ebn0, seed=1):
     return np.ascontiguousarray(llr[:, inv]), s
 
 
-def _decode(modcod, Y, prec="f32", n_ite=10, norm=1.0, early_stop=True):
+def _decode(modcod, Y, prec="f32", n_ite=10, norm=1.0, early_stop=True, compaction=True):
     from dvbs2_b200 import Decoder_LDPC_DVBS2_cuda, Handle
 
     F = Y.shape[0]
-    h = Handle(modcod=modcod, n_ite=n_ite, norm=norm, precision=prec, early_stop=early_stop, n_frames=F)
+    h = Handle(modcod=modcod, n_ite=n_ite, norm=norm, precision=prec, early_stop=early_stop, n_frames=F,
+               compaction=compaction)
     dec = Decoder_LDPC_DVBS2_cuda(h, F)
     V = np.zeros((F, dec.K), np.int32)
     cwd = np.zeros(F, np.int8)
@@ -110,3 +111,38 @@ def test_large_batch_round_trip(oracle):
     assert (cwd == 1).all() and (nit == 1).all()
     assert np.array_equal(V, np.tile(s["bch"], (reps, 1)))
     assert st["frames"] == 16 * reps
+
+
+@pytest.mark.parametrize("modcod,ebn0,prec,F", [("QPSK-S_8/9", 4.0, "f32", 330), ("QPSK-S_8/9", 4.1, "i16", 200),
+                                                ("8PSK-S_3/5", 4.1, "f32", 200), ("QPSK-S_8/9", 4.0, "i8", 300),
+                                                ("8PSK-S_8/9", 7.0, "f32", 257)])
+def test_frame_compaction_is_transparent(oracle, modcod, ebn0, prec, F):
+    """Stragglers are moved to dense groups for their remaining iterations: bits, CWD, iteration counts and counters must
+    equal both the in-place decoder (compaction off) and the oracle."""
+    Y, _ = _llrs(oracle, modcod, F, ebn0, seed=77)
+    if prec != "f32":
+        Y = oracle.quantize(Y, 1 if prec == "i8" else 2, 6, prec)
+    kw = dict(prec=prec)
+    K = MODCODS[modcod]["N_bch"]
+    V1, c1, n1, s1 = _decode(modcod, Y, compaction=True, **kw) if prec != "i8" else _decode_i8(modcod, Y, True)
+    V0, c0, n0, s0 = _decode(modcod, Y, compaction=False, **kw) if prec != "i8" else _decode_i8(modcod, Y, False)
+    assert np.array_equal(V1, V0) and np.array_equal(c1, c0) and np.array_equal(n1, n0)
+    for k in ("frames", "ldpc_iterations", "ldpc_failures"):
+        assert s1[k] == s0[k], k
+    Vo, co, no = oracle.ldpc_decode(K, Y, prec=prec)
+    assert np.array_equal(V1, Vo) and np.array_equal(c1, co) and np.array_equal(n1, no)
+    assert n1.min() < n1.max()  # iteration counts really diverge, so frames were handed over
+    assert s1["kernel_launches"] > s0["kernel_launches"]
+
+
+def _decode_i8(modcod, Y, compaction):
+    from dvbs2_b200 import Decoder_LDPC_DVBS2_cuda, Handle
+
+    F = Y.shape[0]
+    h = Handle(modcod=modcod, precision="i8", quant_dec=1, n_frames=F, compaction=compaction)
+    dec = Decoder_LDPC_DVBS2_cuda(h, F)
+    V, cwd, nit = np.zeros((F, dec.K), np.int32), np.zeros(F, np.int8), np.zeros(F, np.int32)
+    dec.decode_siho(Y, cwd, V, nit)
+    st = h.stats()
+    h.close()
+    return V, cwd, nit, st
