@@ -53,6 +53,9 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-compaction", action="store_true")
+    p.add_argument("--rounds", type=int, default=0, help="decoding rounds (frame compaction between rounds); 0 = library default")
+    p.add_argument("--exit-eighths", type=int, default=0, help="hand-over threshold in eighths of a group; 0 = library default")
+    p.add_argument("--nf-later", type=int, default=0, help="f32: frames per lane in rounds >= 2; 0 = library default")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--cpu-threads", type=int, default=0)
     return p.parse_args()
@@ -227,8 +230,9 @@ def main():
     F = args.frames if args.frames > 0 else sms * 12 * 64
     NB = 2  # input batches rotated between steps (each is far larger than the 126 MB L2)
 
-    h = Handle(modcod=modcod, n_ite=args.ite, norm=1.0, precision=args.prec, early_stop=True, n_frames=F, device=local,
-               compaction=not args.no_compaction)
+    tune = dict(compaction=not args.no_compaction, compaction_rounds=args.rounds, compaction_exit_eighths=args.exit_eighths,
+                compaction_nf_later=args.nf_later)
+    h = Handle(modcod=modcod, n_ite=args.ite, norm=1.0, precision=args.prec, early_stop=True, n_frames=F, device=local, **tune)
     chain = Decoder_chain_DVBS2_cuda(h, F)
     # synthetic frames made where they are decoded: random payload -> BB scramble -> BCH -> LDPC -> interleave -> map -> AWGN
     tx = Transmitter_DVBS2_cuda(h, F)
@@ -328,7 +332,7 @@ def main():
         clones = []
         for c in range(NC):
             hc = Handle(modcod=modcod, n_ite=args.ite, norm=1.0, precision=args.prec, early_stop=True, n_frames=Fe, device=local,
-                        compaction=not args.no_compaction)
+                        **tune)
             hs = torch.empty(Fe, dtype=torch.float32).pin_memory()
             hx = torch.empty((Fe, 2 * n_sym), dtype=torch.float32).pin_memory()
             hV = torch.empty((Fe, K_bch), dtype=torch.int32).pin_memory()

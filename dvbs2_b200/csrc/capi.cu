@@ -72,9 +72,14 @@ struct dvbs2_cuda_handle
     BchDevTables bch{};
     // decoder state
     DevBuf var, cn, hd, out_hd, rem, nz, cwd_ldpc, cwd_bch, nit, stats;
-    // frame compaction: slots [max_frames, max_frames + ext_cap) of var/cn/hd/out_hd hold the survivors of round 1
-    DevBuf surv_mask, surv_iters, dst_base, src_of_dst, dst_iters, n_surv;
-    int ext_cap = 0;
+    // frame compaction (multi-round decoding).  var/cn: region A = slots [0, max_frames) (rounds 1, 3), region B =
+    // [max_frames, max_frames + ext_cap) (rounds 2, 4).  hd/out_hd and the per-slot bookkeeping live in one slot space:
+    // round 1 at [0, max_frames), later rounds in [max_frames, max_frames + ext_slots).
+    DevBuf surv_mask, surv_iters, dst_base, src_of_dst, slot_frame, slot_iters, final_loc, n_surv;
+    int ext_cap = 0, ext_slots = 0;
+    int rounds = 1;       // decoding rounds (1 = no compaction)
+    int exit_eighths = 4; // a group hands its live frames over once fewer than exit_eighths/8 of its frames still iterate
+    int nf_later = 1;     // frames per lane in rounds >= 2
     // staging for the host-buffer entry points (grown on demand, never beyond max_frames)
     DevBuf in_a, in_b, out_a, sigma;
     // transmitter / monitor (allocated on first use)
@@ -232,14 +237,32 @@ demap_args(dvbs2_cuda_handle* h, const float* d_sigma, const float* d_sym, int n
     return d;
 }
 
-// LDPC decode of slots [first_frame, first_frame + n_frames): one round, or two rounds with frame compaction in between
+// Slot-space offsets of a chunk that starts at frame f0 (a multiple of 256; chunks are >= 2048 frames long except the
+// last): the regions of different chunks must be disjoint because chunks run concurrently on the pipeline streams.
+// A chunk of n frames needs < n * e + 128 slots of region B (e = exit_eighths / 8) and < n * (e + e^2 + e^3) + 384 slots
+// of the later rounds' hd / out_hd / bookkeeping space.
+size_t
+region_b_offset(const dvbs2_cuda_handle* h, int f0)
+{
+    // exit_eighths = 4 (the default): n / 2 slots suffice for a chunk of n frames (n a multiple of 256), no padding
+    if (h->exit_eighths == 4) return (size_t)f0 / 2;
+    return ((size_t)f0 * h->exit_eighths / 8 + 255) / 256 * 256 + (size_t)384 * (f0 / 2048);
+}
+size_t
+ext_slot_offset(const dvbs2_cuda_handle* h, int f0)
+{
+    const size_t e = h->exit_eighths; // n * (e/8 + e^2/64 + e^3/512), rounded up
+    return (((size_t)f0 * (64 * e + 8 * e * e + e * e * e) + 511) / 512 + 255) / 256 * 256 + (size_t)768 * (f0 / 2048);
+}
+
+// LDPC decode of slots [first_frame, first_frame + n_frames): one round, or several rounds with frame compaction in
+// between (at most h->rounds; a round is worth launching only while the previous one had at least two groups)
 int
 run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frames, int8_t* d_cwd, int32_t* d_nit)
 {
     LdpcLaunch a = ldpc_args(h, s, first_frame, n_frames, d_cwd, d_nit);
-    const int gsz = 32 * h->nf;
-    const bool two_rounds = h->ext_cap > 0 && h->cfg.early_stop && h->cfg.n_ite >= 4 && a.n_groups >= 2;
-    if (!two_rounds)
+    const bool multi = h->rounds > 1 && h->ext_cap > 0 && h->cfg.early_stop && h->cfg.n_ite >= 4 && a.n_groups >= 2;
+    if (!multi)
     {
         CU(h, launch_ldpc_decode(a, h->cfg.precision, s));
         h->launches += 1;
@@ -248,38 +271,73 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
     int slot = 0;
     for (int i = 0; i < N_PIPE; i++)
         if (s == h->pipe[i]) slot = 1 + i;
-    // round 1: a group hands its live frames over once fewer than half of its frames are still iterating
-    a.exit_below = gsz / 2;
-    a.surv_mask = (uint32_t*)h->surv_mask.p + first_frame / 32;
+    const size_t F = (size_t)h->max_frames;
+    const size_t vb = F + region_b_offset(h, first_frame);     // region B of this chunk (var / cn slots)
+    size_t hs = F + ext_slot_offset(h, first_frame);           // next free slot of the later rounds' slot space
+    uint32_t* const out_hd0 = a.out_hd;                        // round-1 subgroups of this chunk: the merge target
+    uint32_t* const mask0 = (uint32_t*)h->surv_mask.p + first_frame / 32;
+    int* const final_loc = (int*)h->final_loc.p + first_frame;
+    const int n_groups0 = a.n_groups;
+
+    // round 1 (in place), then compaction + round r for r = 2..rounds
+    a.nf = h->nf;
+    a.exit_below = 32 * h->nf * h->exit_eighths / 8;
+    a.surv_mask = mask0;
     a.surv_iters = (int*)h->surv_iters.p + first_frame;
     CU(h, launch_ldpc_decode(a, h->cfg.precision, s));
-    // survivors -> dense groups in the extension region (each group exports < gsz/2 frames, so < n_frames/2 in total)
-    const size_t ext0 = (size_t)h->max_frames + first_frame / 2; // multiple of gsz: first_frame is a multiple of 256
-    const int e0 = first_frame / 2;
-    const int cap = std::min(h->ext_cap - e0, (a.n_groups * (gsz / 2) + gsz - 1) / gsz * gsz);
-    CompactLaunch c{};
-    c.surv_mask = a.surv_mask, c.surv_iters = a.surv_iters;
-    c.dst_base = (int*)h->dst_base.p + first_frame / gsz;
-    c.n_surv = (int*)h->n_surv.p + slot;
-    c.src_of_dst = (int*)h->src_of_dst.p + e0, c.dst_iters = (int*)h->dst_iters.p + e0;
-    c.var_src = a.var, c.var_dst = (char*)h->var.p + ext0 * N_LDPC * h->elt;
-    c.cn_src = a.cn, c.cn_dst = (uint4*)h->cn.p + ext0 * h->mc.M;
-    c.out_hd_src = a.out_hd, c.out_hd_dst = (uint32_t*)h->out_hd.p + (ext0 / 32) * N_LDPC;
-    c.n_groups = a.n_groups, c.nf = h->nf, c.cap = cap, c.M = h->mc.M;
-    c.nf_dst = ldpc_round2_frames_per_lane(h->cfg.precision);
-    CU(h, launch_compact(c, h->cfg.precision, s));
-    // round 2: the survivors, to the end of their iteration budget
-    LdpcLaunch b = a;
-    b.var = c.var_dst, b.cn = c.cn_dst;
-    b.hd = (uint32_t*)h->hd.p + (ext0 / 32) * N_LDPC;
-    b.out_hd = (uint32_t*)h->out_hd.p + (ext0 / 32) * N_LDPC;
-    b.queue = h->d_queue + 8 + slot;
-    b.n_frames = cap, b.n_groups = cap / (32 * c.nf_dst), b.nf = c.nf_dst;
-    b.n_slots_dev = c.n_surv, b.slot_frame = c.src_of_dst, b.slot_iters = c.dst_iters;
-    b.surv_mask = nullptr, b.surv_iters = nullptr, b.exit_below = 0;
-    CU(h, launch_ldpc_decode(b, h->cfg.precision, s));
-    CU(h, launch_merge_back(c, s));
-    h->launches += 6;
+    h->launches += 1;
+    LdpcLaunch prev = a;
+    size_t prev_hs = (size_t)first_frame; // slot-space index of prev's slot 0
+    const int* prev_frame = nullptr;
+    const int* prev_n_slots = nullptr;
+    for (int r = 2; r <= h->rounds && prev.n_groups >= 2; r++)
+    {
+        const int nf = ldpc_later_frames_per_lane(h->cfg.precision, h->nf_later);
+        const int gsz = 32 * nf;
+        // every group of the previous round hands over fewer than exit_below frames
+        const int cap = (prev.n_groups * (prev.exit_below - 1) + gsz - 1) / gsz * gsz;
+        const bool to_b = (r % 2) == 0;
+        const size_t vslot = to_b ? vb : (size_t)first_frame;
+        if ((to_b ? (vb - F + cap > (size_t)h->ext_cap) : (cap > n_frames + 32 * h->nf)) || hs - F + cap > (size_t)h->ext_slots)
+        { // cannot happen by construction; frames already handed over would be lost, so fail loudly
+            h->last_error = "frame compaction: region overflow";
+            return DVBS2_ERR_INVALID;
+        }
+        CompactLaunch c{};
+        c.surv_mask = prev.surv_mask, c.surv_iters = prev.surv_iters, c.src_frame = prev_frame, c.n_src_slots = prev_n_slots;
+        c.dst_base = (int*)h->dst_base.p + prev_hs / 32;
+        c.n_surv = (int*)h->n_surv.p + 8 * (r - 2) + slot;
+        c.src_of_dst = (int*)h->src_of_dst.p + hs;
+        c.dst_frame = (int*)h->slot_frame.p + hs;
+        c.dst_iters = (int*)h->slot_iters.p + hs;
+        c.final_loc = final_loc;
+        c.dst_slot0 = (int)(hs - first_frame);
+        c.var_src = prev.var, c.var_dst = (char*)h->var.p + vslot * N_LDPC * h->elt;
+        c.cn_src = prev.cn, c.cn_dst = (uint4*)h->cn.p + vslot * h->mc.M;
+        c.n_groups = prev.n_groups, c.nf = prev.nf, c.cap = cap, c.M = h->mc.M, c.nf_dst = nf;
+        CU(h, launch_compact(c, h->cfg.precision, s));
+
+        LdpcLaunch b = a;
+        b.var = c.var_dst, b.cn = c.cn_dst;
+        b.hd = (uint32_t*)h->hd.p + (hs / 32) * N_LDPC;
+        b.out_hd = (uint32_t*)h->out_hd.p + (hs / 32) * N_LDPC;
+        b.queue = h->d_queue + 8 * (r - 1) + slot;
+        b.n_frames = cap, b.n_groups = cap / gsz, b.nf = nf;
+        b.n_slots_dev = c.n_surv, b.slot_frame = c.dst_frame, b.slot_iters = c.dst_iters;
+        const bool last = r == h->rounds || b.n_groups < 2;
+        b.exit_below = last ? 0 : gsz * h->exit_eighths / 8;
+        b.surv_mask = last ? nullptr : (uint32_t*)h->surv_mask.p + hs / 32;
+        b.surv_iters = last ? nullptr : (int*)h->surv_iters.p + hs;
+        CU(h, launch_ldpc_decode(b, h->cfg.precision, s));
+        h->launches += 4;
+        prev = b, prev_hs = hs, prev_frame = c.dst_frame, prev_n_slots = c.n_surv;
+        hs += cap;
+        if (last) break;
+    }
+    MergeLaunch m{};
+    m.surv_mask = mask0, m.final_loc = final_loc, m.out_hd = out_hd0, m.n_groups = n_groups0, m.nf = h->nf;
+    CU(h, launch_merge_back(m, s));
+    h->launches += 1;
     return DVBS2_OK;
 }
 
@@ -443,7 +501,8 @@ extern "C"
         if (!h) return DVBS2_OK;
         cudaSetDevice(h->cfg.device);
         for (DevBuf* b : { &h->var, &h->cn, &h->hd, &h->out_hd, &h->rem, &h->nz, &h->cwd_ldpc, &h->cwd_bch, &h->nit,
-                           &h->stats, &h->surv_mask, &h->surv_iters, &h->dst_base, &h->src_of_dst, &h->dst_iters, &h->n_surv,
+                           &h->stats, &h->surv_mask, &h->surv_iters, &h->dst_base, &h->src_of_dst, &h->slot_frame, &h->slot_iters,
+                           &h->final_loc, &h->n_surv,
                            &h->in_a, &h->in_b, &h->out_a, &h->sigma, &h->tx_src, &h->tx_cw, &h->tx_scr,
                            &h->tx_gmask, &h->mon })
             if (b->p) cudaFree(b->p);
@@ -549,15 +608,21 @@ extern "C"
         memcpy(h->bch.synd_mat, bt.synd_mat, sizeof(bt.synd_mat));
 
         const size_t G = (size_t)h->max_groups, F = (size_t)h->max_frames;
-        const int gsz = 32 * h->nf;
-        h->ext_cap = cfg->no_compaction ? 0 : (h->max_frames / 2 + gsz - 1) / gsz * gsz + gsz;
-        const size_t FE = F + h->ext_cap, GE = FE / 32; // slots incl. the compaction region
+        // multi-round decoding: rounds / hand-over threshold / later-round group width (0 = defaults)
+        h->rounds = cfg->no_compaction ? 1 : (cfg->compaction_rounds > 0 ? std::min(cfg->compaction_rounds, 4) : 2);
+        h->exit_eighths = cfg->compaction_exit_eighths > 0 ? std::min(cfg->compaction_exit_eighths, 6) : 4;
+        h->nf_later = ldpc_later_frames_per_lane(cfg->precision, cfg->compaction_nf_later);
+        h->ext_cap = h->rounds > 1 ? (int)region_b_offset(h, (h->max_frames + 255) / 256 * 256) + 512 : 0;
+        h->ext_slots = h->rounds > 1 ? (int)ext_slot_offset(h, (h->max_frames + 255) / 256 * 256) + 1024 : 0;
+        const size_t FE = F + h->ext_cap;                    // var / cn slots
+        const size_t FS = F + h->ext_slots, GS = FS / 32;    // hd / out_hd / bookkeeping slots
         int rc;
         if ((rc = ensure(h, h->var, FE * N_LDPC * h->elt)) || (rc = ensure(h, h->cn, FE * mc.M * sizeof(uint4))) ||
-            (rc = ensure(h, h->hd, GE * N_LDPC * 4)) || (rc = ensure(h, h->out_hd, GE * N_LDPC * 4)) ||
-            (rc = ensure(h, h->surv_mask, G * 4 + 4)) || (rc = ensure(h, h->surv_iters, F * 4 + 4)) ||
-            (rc = ensure(h, h->dst_base, G * 4 + 4)) || (rc = ensure(h, h->src_of_dst, (size_t)h->ext_cap * 4 + 4)) ||
-            (rc = ensure(h, h->dst_iters, (size_t)h->ext_cap * 4 + 4)) || (rc = ensure(h, h->n_surv, 8 * sizeof(int))) ||
+            (rc = ensure(h, h->hd, GS * N_LDPC * 4)) || (rc = ensure(h, h->out_hd, GS * N_LDPC * 4)) ||
+            (rc = ensure(h, h->surv_mask, GS * 4 + 4)) || (rc = ensure(h, h->surv_iters, FS * 4 + 4)) ||
+            (rc = ensure(h, h->dst_base, GS * 4 + 4)) || (rc = ensure(h, h->src_of_dst, FS * 4 + 4)) ||
+            (rc = ensure(h, h->slot_frame, FS * 4 + 4)) || (rc = ensure(h, h->slot_iters, FS * 4 + 4)) ||
+            (rc = ensure(h, h->final_loc, F * 4 + 4)) || (rc = ensure(h, h->n_surv, 32 * sizeof(int))) ||
             (rc = ensure(h, h->rem, G * BCH_NPOLY * GF_M * 4)) || (rc = ensure(h, h->nz, G * 4)) ||
             (rc = ensure(h, h->cwd_ldpc, F)) || (rc = ensure(h, h->cwd_bch, F)) || (rc = ensure(h, h->nit, F * 4)) ||
             (rc = ensure(h, h->stats, STAT_COUNT * sizeof(unsigned long long))))

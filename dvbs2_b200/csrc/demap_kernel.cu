@@ -21,10 +21,14 @@ namespace dvbs2
 {
 namespace
 {
+// max*(a,b) = max(a,b) + log(1 + exp(-|a-b|)) (max.hxx:29-36).  The correction term lies in (0, ln 2]; it is evaluated
+// with the SFU approximations (ex2.approx / lg2.approx, absolute error below 1e-6 here), as the reference's own SIMD body
+// evaluates it with MIPP's polynomial exp/log rather than libm (Modem_generic_fast.hxx:72-138).  The precise
+// expf/log1pf pair made this kernel ALU-bound at 4x its streaming time.
 __device__ __forceinline__ float
 max_star(float a, float b)
 {
-    return fmaxf(a, b) + log1pf(expf(-fabsf(a - b)));
+    return fmaxf(a, b) + __logf(1.0f + __expf(-fabsf(a - b)));
 }
 
 // LLRs of one received symbol: out[b], b = 0..BPS-1
@@ -42,14 +46,22 @@ demap_symbol(float yr, float yi, float inv, const float* __restrict__ cs, float*
 #pragma unroll
     for (int b = 0; b < BPS; b++)
     {
-        float L0 = -INFINITY, L1 = -INFINITY;
+        // max*(-inf, x) = x: the first point of each class starts the accumulation (resolved at compile time)
+        float L0 = 0.f, L1 = 0.f;
+        bool h0 = false, h1 = false;
 #pragma unroll
         for (int j = 0; j < (1 << BPS); j++)
         {
             if (((j >> b) & 1) == 0)
-                L0 = max_star(L0, d[j]);
+            {
+                L0 = h0 ? max_star(L0, d[j]) : d[j];
+                h0 = true;
+            }
             else
-                L1 = max_star(L1, d[j]);
+            {
+                L1 = h1 ? max_star(L1, d[j]) : d[j];
+                h1 = true;
+            }
         }
         out[b] = L0 - L1;
     }
@@ -99,46 +111,96 @@ demap_frames_kernel(const DemapLaunch a, float* __restrict__ llr, int deinterlea
         o[deinterleave ? natural_pos(k, b, BPS, a.n_sym, a.itl_cols, a.itl_rev) : k * BPS + b] = out[b];
 }
 
-// warp = (subgroup of 32 frames, 16 consecutive symbols); lane = frame.  Symbols are staged through shared memory so the
-// global reads are 128-byte rows of one frame and the global writes are 32-lane rows of one variable.
-constexpr int DEMAP_WARPS = 4;
-template<int BPS, typename R>
-__global__ void __launch_bounds__(DEMAP_WARPS * 32) demap_to_var_kernel(const DemapLaunch a, R* __restrict__ var, int nf)
+// NF values of R as one 4- or 8-byte store
+template<typename R, int NF>
+struct LaneVec;
+template<>
+struct LaneVec<float, 2>
 {
+    using T = float2;
+    __device__ static T make(const float* x) { return make_float2(x[0], x[1]); }
+};
+template<>
+struct LaneVec<int16_t, 2>
+{
+    using T = uint32_t;
+    __device__ static T make(const int16_t* x) { return (uint32_t)(uint16_t)x[0] | ((uint32_t)(uint16_t)x[1] << 16); }
+};
+template<>
+struct LaneVec<int8_t, 4>
+{
+    using T = uint32_t;
+    __device__ static T make(const int8_t* x)
+    {
+        return (uint32_t)(uint8_t)x[0] | ((uint32_t)(uint8_t)x[1] << 8) | ((uint32_t)(uint8_t)x[2] << 16) | ((uint32_t)(uint8_t)x[3] << 24);
+    }
+};
+
+// warp = (decoder group of 32*NF frames, 16 consecutive symbols); lane l demaps frames l, 32+l, ... of the group.
+// Symbols are staged through shared memory so the global reads are 128-byte rows of one frame and every global write
+// is one full row var[group][v][0..31][0..NF-1] of the decoder's layout (256 B for float).
+template<int NF>
+struct DemapCfg
+{
+    static constexpr int WARPS = 8 / NF; // 33.8 KB of shared memory per block for every NF
+};
+template<int BPS, typename R, int NF>
+__global__ void __launch_bounds__(DemapCfg<NF>::WARPS * 32) demap_to_var_kernel(const DemapLaunch a, R* __restrict__ var)
+{
+    constexpr int WARPS = DemapCfg<NF>::WARPS;
+    using Vec = typename LaneVec<R, NF>::T;
     __shared__ float cs[2 << BPS];
-    __shared__ float tile[DEMAP_WARPS][32][33];
+    __shared__ float tile[WARPS][NF][32][33];
     if (threadIdx.x < (2 << BPS)) cs[threadIdx.x] = a.cstl[threadIdx.x];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.y;
-    const int k0 = (blockIdx.x * DEMAP_WARPS + warp) * 16;
+    const int g = blockIdx.y; // decoder group
+    const int k0 = (blockIdx.x * WARPS + warp) * 16;
     if (k0 >= a.n_sym) return;
     const int nfl = 2 * a.n_sym;
-    for (int j = 0; j < 32; j++)
-    {
-        const int f = g * 32 + j, e = 2 * k0 + lane;
-        tile[warp][j][lane] = (f < a.n_frames && e < nfl) ? a.sym[(size_t)f * nfl + e] : 0.f;
-    }
+    const int e = 2 * k0 + lane;
+#pragma unroll
+    for (int j = 0; j < NF; j++)
+#pragma unroll 16
+        for (int r = 0; r < 32; r++)
+        {
+            const int f = (g * NF + j) * 32 + r;
+            tile[warp][j][r][lane] = (f < a.n_frames && e < nfl) ? __ldg(a.sym + (size_t)f * nfl + e) : 0.f;
+        }
     __syncwarp();
-    const int frame = g * 32 + lane;
-    const float sg = frame < a.n_frames ? a.sigma[frame] : 1.f;
-    const float inv = 1.0f / (2 * sg * sg);
+    float inv[NF];
+    bool live[NF];
+#pragma unroll
+    for (int j = 0; j < NF; j++)
+    {
+        const int frame = (g * NF + j) * 32 + lane;
+        live[j] = frame < a.n_frames;
+        const float sg = live[j] ? a.sigma[frame] : 1.f;
+        inv[j] = 1.0f / (2 * sg * sg);
+    }
     const float factor = (float)(1 << a.quant_dec);
     const float vmax = (float)((1 << (a.quant_bits - 1)) - 1);
-    // subgroup g = group g / nf, slot g % nf of the decoder's var[group][v][lane][nf] layout
-    R* vg = var + ((size_t)(g / nf) * N_LDPC * 32 + lane) * nf + g % nf;
-#pragma unroll 4
+    Vec* vg = reinterpret_cast<Vec*>(var) + (size_t)g * N_LDPC * 32 + lane;
+#pragma unroll 2
     for (int s = 0; s < 16; s++)
     {
         const int k = k0 + s;
         if (k >= a.n_sym) break;
-        float out[BPS];
-        demap_symbol<BPS>(tile[warp][lane][2 * s], tile[warp][lane][2 * s + 1], inv, cs, out);
+        R q[BPS][NF];
+#pragma unroll
+        for (int j = 0; j < NF; j++)
+        {
+            float out[BPS];
+            demap_symbol<BPS>(tile[warp][j][lane][2 * s], tile[warp][j][lane][2 * s + 1], inv[j], cs, out);
+#pragma unroll
+            for (int b = 0; b < BPS; b++)
+                q[b][j] = live[j] ? quantize<R>(out[b], factor, vmax) : (R)0;
+        }
 #pragma unroll
         for (int b = 0; b < BPS; b++)
         {
             const int v = natural_pos(k, b, BPS, a.n_sym, a.itl_cols, a.itl_rev);
-            vg[(size_t)v * 32 * nf] = frame < a.n_frames ? quantize<R>(out[b], factor, vmax) : (R)0;
+            vg[(size_t)v * 32] = LaneVec<R, NF>::make(q[b]);
         }
     }
 }
@@ -176,17 +238,27 @@ launch_demap_frames(const DemapLaunch& a, float* llr, int deinterleave, cudaStre
     return cudaGetLastError();
 }
 
+template<int BPS, typename R, int NF>
+static void
+demap_to_var_launch(const DemapLaunch& a, void* var, cudaStream_t s)
+{
+    constexpr int WARPS = DemapCfg<NF>::WARPS;
+    const int groups = (a.n_frames + 32 * NF - 1) / (32 * NF); // whole decoder groups: pad frames get zeros
+    const dim3 grid((a.n_sym + 16 * WARPS - 1) / (16 * WARPS), groups);
+    demap_to_var_kernel<BPS, R, NF><<<grid, WARPS * 32, 0, s>>>(a, (R*)var);
+}
+
 template<int BPS>
 static cudaError_t
 demap_to_var_bps(const DemapLaunch& a, void* var, int precision, int nf, cudaStream_t s)
 {
-    const int groups = (a.n_frames + 32 * nf - 1) / (32 * nf) * nf; // whole decoder groups: pad subgroups get zeros
-    const dim3 grid((a.n_sym + 16 * DEMAP_WARPS - 1) / (16 * DEMAP_WARPS), groups);
+    // the group width is fixed by the precision (ldpc_frames_per_lane): 2 for float and int16, 4 for int8
+    if (nf != (precision == 2 ? 4 : 2)) return cudaErrorInvalidValue;
     switch (precision)
     {
-        case 0: demap_to_var_kernel<BPS, float><<<grid, DEMAP_WARPS * 32, 0, s>>>(a, (float*)var, nf); break;
-        case 1: demap_to_var_kernel<BPS, int16_t><<<grid, DEMAP_WARPS * 32, 0, s>>>(a, (int16_t*)var, nf); break;
-        case 2: demap_to_var_kernel<BPS, int8_t><<<grid, DEMAP_WARPS * 32, 0, s>>>(a, (int8_t*)var, nf); break;
+        case 0: demap_to_var_launch<BPS, float, 2>(a, var, s); break;
+        case 1: demap_to_var_launch<BPS, int16_t, 2>(a, var, s); break;
+        case 2: demap_to_var_launch<BPS, int8_t, 4>(a, var, s); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

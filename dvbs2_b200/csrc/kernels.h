@@ -45,39 +45,51 @@ struct LdpcLaunch
     int k8; // norm * 8 if that is an integer in 1..8, else 0
     int early_stop;
     int n_sms;
-    // two-round decoding (frame compaction): all null / 0 for a plain single-round launch
-    const int* n_slots_dev;  // round 2: number of occupied slots, known only on the device (n_frames = capacity)
-    const int* slot_frame;   // round 2: [slots] frame index (for cwd / n_iter) of each slot
-    const int* slot_iters;   // round 2: [slots] iterations already spent; such frames carry check state
-    uint32_t* surv_mask;     // round 1: [subgroups] lanes handed over to round 2 (0 if none)
-    int* surv_iters;         // round 1: [slots] iterations spent by the lanes handed over
-    int exit_below;          // round 1: hand the group's live frames over once fewer than this many remain (0 = never)
+    // multi-round decoding (frame compaction): all null / 0 for a plain single-round launch
+    const int* n_slots_dev;  // rounds >= 2: number of occupied slots, known only on the device (n_frames = capacity)
+    const int* slot_frame;   // rounds >= 2: [slots] frame index (for cwd / n_iter) of each slot
+    const int* slot_iters;   // rounds >= 2: [slots] iterations already spent; such frames carry check state
+    uint32_t* surv_mask;     // [subgroups] lanes handed over to the next round (0 if none); null in the last round
+    int* surv_iters;         // [slots] iterations spent by the lanes handed over
+    int exit_below;          // hand the group's live frames over once fewer than this many remain (0 = never)
     int nf;                  // frames per lane of this launch (0 = ldpc_frames_per_lane(precision))
 };
 
-// Frame compaction between the two rounds: survivors of round 1 (src slots) are packed, in slot order, into dense groups
-// of fresh slots (dst), their var / check state copied; after round 2 their hard decisions return to the src subgroups.
+// Frame compaction between two rounds: survivors of round r (src slots) are packed, in slot order, into dense groups of
+// fresh slots (dst) for round r+1, their var / check state copied.  After the last round one merge pass returns every
+// handed-over frame's hard decisions to the bit lane of its round-1 subgroup (final_loc says where they ended up).
 struct CompactLaunch
 {
-    const uint32_t* surv_mask; // [n_groups * nf]
+    const uint32_t* surv_mask; // [n_groups * nf]   of the source round
     const int* surv_iters;     // [n_groups * nf * 32]
+    const int* src_frame;      // [n_groups * nf * 32] frame index of each source slot, or null (round 1: slot = frame)
+    const int* n_src_slots;    // device: occupied source slots (null: all n_groups groups are occupied)
     int* dst_base;             // [n_groups]   exclusive prefix of survivors per group
     int* n_surv;               // [1]
-    int* src_of_dst;           // [cap]        source slot of each destination slot (= frame index for the outputs)
+    int* src_of_dst;           // [cap]        source slot of each destination slot
+    int* dst_frame;            // [cap]        frame index of each destination slot
     int* dst_iters;            // [cap]
+    int* final_loc;            // [frames]     out_hd slot (dst_slot0 + d) holding the frame's final hard decisions
+    int dst_slot0;             // index of destination slot 0 in the out_hd slot space of the merge pass
     const void* var_src;
     void* var_dst;
     const uint4* cn_src;
     uint4* cn_dst;
-    uint32_t* out_hd_src;      // [n_groups * nf][16200]  round-1 slots (merge target)
-    const uint32_t* out_hd_dst; // [cap / 32][16200]
     int n_groups, nf, cap, M;
-    int nf_dst;                // frames per lane of the destination groups (round 2 may use narrower groups: its few
-                               // warps are latency-bound, so halving the work per check halves its duration)
+    int nf_dst;                // frames per lane of the destination groups (<= nf)
 };
-int ldpc_round2_frames_per_lane(int precision); // 1 (f32), else as round 1
+// merge pass: round-1 subgroups pull the final bits of the frames they handed over
+struct MergeLaunch
+{
+    const uint32_t* surv_mask; // [n_groups * nf]  round 1
+    const int* final_loc;      // [frames]
+    uint32_t* out_hd;          // [slot space / 32][16200]; round-1 subgroups first
+    int n_groups, nf;
+};
 cudaError_t launch_compact(const CompactLaunch& c, int precision, cudaStream_t s);    // scan + expand + copy (3 kernels)
-cudaError_t launch_merge_back(const CompactLaunch& c, cudaStream_t s);
+cudaError_t launch_merge_back(const MergeLaunch& c, cudaStream_t s);
+// frames per lane allowed for round r >= 2 given the handle's preference (0 = default)
+int ldpc_later_frames_per_lane(int precision, int preferred);
 
 int ldpc_frames_per_lane(int precision); // NF: 2 (f32, i16), 4 (i8)
 cudaError_t launch_ldpc_decode(const LdpcLaunch& a, int precision, cudaStream_t s);

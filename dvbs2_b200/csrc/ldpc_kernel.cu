@@ -424,10 +424,17 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
             __syncwarp();
             // ---- hand the stragglers over to the compaction step once most of the group has converged: they continue in
             //      a dense group instead of keeping this warp (and its 256-byte chunks) busy for a few live lanes
-            if (a.exit_below > 0 && n_active > 0 && n_active < a.exit_below && a.n_ite - (ite + 1) >= 2)
+            if (a.exit_below > 0 && n_active > 0 && n_active < a.exit_below)
             {
-                exported = true;
-                break;
+                int left = 0; // iterations the group's live frames may still run (they differ after a compaction)
+#pragma unroll
+                for (int j = 0; j < NF; j++)
+                    if ((active[j] >> lane) & 1) left = max(left, a.n_ite - my_iters[j]);
+                if (__reduce_max_sync(FULL, left) >= 2)
+                {
+                    exported = true;
+                    break;
+                }
             }
         }
 
@@ -470,6 +477,14 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
 }
 
 // ---------------------------------------------------------------------------------------------- frame compaction
+__device__ __forceinline__ int
+occupied_groups(const CompactLaunch& c)
+{
+    if (!c.n_src_slots) return c.n_groups;
+    const int per = 32 * c.nf;
+    return min(c.n_groups, (*c.n_src_slots + per - 1) / per);
+}
+
 // survivors per group -> exclusive prefix (one block; groups are few thousand)
 __global__ void __launch_bounds__(1024) compact_scan_kernel(const CompactLaunch c)
 {
@@ -477,11 +492,12 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(const CompactLaunch 
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (int g0 = 0; g0 < c.n_groups; g0 += 1024)
+    const int n_groups = occupied_groups(c);
+    for (int g0 = 0; g0 < n_groups; g0 += 1024)
     {
         const int g = g0 + threadIdx.x;
         int n = 0;
-        if (g < c.n_groups)
+        if (g < n_groups)
             for (int j = 0; j < c.nf; j++)
                 n += __popc(c.surv_mask[g * c.nf + j]);
         part[threadIdx.x] = n;
@@ -493,7 +509,7 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(const CompactLaunch 
             part[threadIdx.x] += v;
             __syncthreads();
         }
-        if (g < c.n_groups) c.dst_base[g] = carry + part[threadIdx.x] - n;
+        if (g < n_groups) c.dst_base[g] = carry + part[threadIdx.x] - n;
         __syncthreads();
         if (threadIdx.x == 1023) carry += part[1023];
         __syncthreads();
@@ -506,7 +522,7 @@ __global__ void
 compact_expand_kernel(const CompactLaunch c)
 {
     const int sg = blockIdx.x * blockDim.x + threadIdx.x;
-    if (sg >= c.n_groups * c.nf) return;
+    if (sg >= occupied_groups(c) * c.nf) return;
     const int g = sg / c.nf, j = sg % c.nf;
     int d = c.dst_base[g];
     for (int k = 0; k < j; k++)
@@ -518,14 +534,18 @@ compact_expand_kernel(const CompactLaunch c)
         m &= m - 1;
         if (d < c.cap)
         {
-            c.src_of_dst[d] = sg * 32 + l;
-            c.dst_iters[d] = c.surv_iters[sg * 32 + l];
+            const int s = sg * 32 + l;
+            const int frame = c.src_frame ? c.src_frame[s] : s;
+            c.src_of_dst[d] = s;
+            c.dst_frame[d] = frame;
+            c.dst_iters[d] = c.surv_iters[s];
+            c.final_loc[frame] = c.dst_slot0 + d;
         }
         d++;
     }
 }
 
-// warp = (destination group, part): gathers the state of its 32*NF survivors.  Survivors of one source group are
+// warp = (destination group, part): gathers the state of its 32*ND survivors.  Survivors of one source group are
 // neighbours in destination order, so the scattered element loads of a warp fall into a handful of source chunks.
 constexpr int COMPACT_PARTS = 8;
 template<typename R, int NF, int ND> // NF: frames per lane of the source groups, ND: of the destination groups
@@ -571,42 +591,40 @@ __global__ void __launch_bounds__(128) compact_copy_kernel(const CompactLaunch c
             cd[(size_t)(k * ND + j) * 32] = valid[j] ? __ldcg(c.cn_src + cbase[j] + (size_t)k * NF * 32) : make_uint4(0u, 0u, 0u, 0u);
 }
 
-// after round 2: the survivors' final hard decisions go back to the bit lanes of their round-1 subgroups.
-// warp = (source group, part), lanes = consecutive variables.
-__global__ void __launch_bounds__(128) merge_back_kernel(const CompactLaunch c)
+// after the last round: the final hard decisions of every frame handed over by round 1 go back to the bit lane of its
+// round-1 subgroup.  warp = (round-1 group, part), lanes = consecutive variables.
+__global__ void __launch_bounds__(128) merge_back_kernel(const MergeLaunch c)
 {
     const int lane = threadIdx.x & 31;
     const int g = blockIdx.x;
     const int part = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (part >= COMPACT_PARTS) return;
-    int d0 = c.dst_base[g];
     const int v0 = (int)((long)N_LDPC * part / COMPACT_PARTS), v1 = (int)((long)N_LDPC * (part + 1) / COMPACT_PARTS);
     for (int j = 0; j < c.nf; j++)
     {
         const unsigned m = c.surv_mask[g * c.nf + j];
-        if (m)
+        if (!m) continue; // warp-uniform
+        const int my_loc = ((m >> lane) & 1) ? c.final_loc[(g * c.nf + j) * 32 + lane] : 0;
+        uint32_t* dst = c.out_hd + (size_t)(g * c.nf + j) * N_LDPC;
+        for (int v0w = v0; v0w < v1; v0w += 32)
         {
-            uint32_t* dst = c.out_hd_src + (size_t)(g * c.nf + j) * N_LDPC;
-            for (int v = v0 + lane; v < v1; v += 32)
+            const int v = v0w + lane;
+            const bool in = v < v1;
+            uint32_t w = in ? dst[v] : 0u;
+            unsigned mm = m;
+            while (mm)
             {
-                uint32_t w = dst[v];
-                unsigned mm = m;
-                int d = d0;
-                while (mm)
+                const int l = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const int loc = __shfl_sync(FULL, my_loc, l);
+                if (in)
                 {
-                    const int l = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    if (d < c.cap)
-                    {
-                        const uint32_t bit = (c.out_hd_dst[(size_t)(d >> 5) * N_LDPC + v] >> (d & 31)) & 1u;
-                        w = (w & ~(1u << l)) | (bit << l);
-                    }
-                    d++;
+                    const uint32_t bit = (c.out_hd[(size_t)(loc >> 5) * N_LDPC + v] >> (loc & 31)) & 1u;
+                    w = (w & ~(1u << l)) | (bit << l);
                 }
-                dst[v] = w;
             }
+            if (in) dst[v] = w;
         }
-        d0 += __popc(m);
     }
 }
 
@@ -729,26 +747,37 @@ launch_compact_t(const CompactLaunch& c, cudaStream_t s)
 }
 
 int
-ldpc_round2_frames_per_lane(int precision)
+ldpc_later_frames_per_lane(int precision, int preferred)
 {
-    return precision == 0 ? 1 : ldpc_frames_per_lane(precision);
+    // float: narrower groups in the later rounds (their few warps are latency-bound, so halving the work per check
+    // halves the time a warp needs per check) unless asked otherwise; integers keep their 4-byte lanes
+    if (precision == 0) return preferred == 2 ? 2 : 1;
+    return ldpc_frames_per_lane(precision);
 }
 
 cudaError_t
 launch_compact(const CompactLaunch& c, int precision, cudaStream_t s)
 {
-    if (c.nf != ldpc_frames_per_lane(precision) || c.nf_dst != ldpc_round2_frames_per_lane(precision)) return cudaErrorInvalidValue;
+    if (c.cap % (32 * c.nf_dst)) return cudaErrorInvalidValue;
     switch (precision)
     {
-        case 0: return launch_compact_t<float, 2, 1>(c, s);
-        case 1: return launch_compact_t<int16_t, 2, 2>(c, s);
-        case 2: return launch_compact_t<int8_t, 4, 4>(c, s);
+        case 0:
+            if (c.nf == 2 && c.nf_dst == 1) return launch_compact_t<float, 2, 1>(c, s);
+            if (c.nf == 2 && c.nf_dst == 2) return launch_compact_t<float, 2, 2>(c, s);
+            if (c.nf == 1 && c.nf_dst == 1) return launch_compact_t<float, 1, 1>(c, s);
+            break;
+        case 1:
+            if (c.nf == 2 && c.nf_dst == 2) return launch_compact_t<int16_t, 2, 2>(c, s);
+            break;
+        case 2:
+            if (c.nf == 4 && c.nf_dst == 4) return launch_compact_t<int8_t, 4, 4>(c, s);
+            break;
     }
     return cudaErrorInvalidValue;
 }
 
 cudaError_t
-launch_merge_back(const CompactLaunch& c, cudaStream_t s)
+launch_merge_back(const MergeLaunch& c, cudaStream_t s)
 {
     const dim3 grid(c.n_groups, (COMPACT_PARTS + 3) / 4);
     merge_back_kernel<<<grid, 128, 0, s>>>(c);

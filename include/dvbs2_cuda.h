@@ -75,10 +75,14 @@ extern "C"
         int device;      /* CUDA device ordinal                                                            */
         int quant_bits;  /* Quantizer_pow2 saturation_pos (AFF3CT default 6), used by int precisions       */
         int quant_dec;   /* Quantizer_pow2 fixed_point_pos (AFF3CT default 2)                              */
-        int no_compaction; /* 0 (default): frames still iterating when most of their 64-frame group has converged are
-                              packed into dense groups for the remaining iterations (same results, fewer bytes);
+        int no_compaction; /* 0 (default): frames still iterating when most of their group has converged are packed
+                              into dense groups for the remaining iterations (same results, fewer bytes moved);
                               1: every frame stays in its group                                                  */
-        int reserved[6]; /* must be 0                                                                      */
+        int compaction_rounds;       /* decoding rounds incl. the first, 2..4 (0 = default 2)                       */
+        int compaction_exit_eighths; /* a group hands its live frames over once fewer than this many eighths of its
+                                        frames still iterate, 1..6 (0 = default 4)                                   */
+        int compaction_nf_later;     /* f32 only: frames per lane in rounds >= 2, 1 or 2 (0 = default 1)            */
+        int reserved[3]; /* must be 0                                                                      */
     } dvbs2_cuda_cfg;
 
     typedef struct

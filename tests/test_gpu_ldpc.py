@@ -7,6 +7,9 @@ from oracle.oracle import MODCODS, N_LDPC, synth_frames
 pytestmark = pytest.mark.gpu
 
 
+_CACHE = {}
+
+
 def _llrs(oracle, modcod, F, ebn0, seed=1):
     s = synth_frames(oracle, modcod, F, ebn0, seed=seed)
     mc = MODCODS[modcod]
@@ -15,12 +18,12 @@ def _llrs(oracle, modcod, F, ebn0, seed=1):
     return np.ascontiguousarray(llr[:, inv]), s
 
 
-def _decode(modcod, Y, prec="f32", n_ite=10, norm=1.0, early_stop=True, compaction=True):
+def _decode(modcod, Y, prec="f32", n_ite=10, norm=1.0, early_stop=True, compaction=True, **cfg):
     from dvbs2_b200 import Decoder_LDPC_DVBS2_cuda, Handle
 
     F = Y.shape[0]
     h = Handle(modcod=modcod, n_ite=n_ite, norm=norm, precision=prec, early_stop=early_stop, n_frames=F,
-               compaction=compaction)
+               compaction=compaction, **cfg)
     dec = Decoder_LDPC_DVBS2_cuda(h, F)
     V = np.zeros((F, dec.K), np.int32)
     cwd = np.zeros(F, np.int8)
@@ -133,6 +136,37 @@ def test_frame_compaction_is_transparent(oracle, modcod, ebn0, prec, F):
     assert np.array_equal(V1, Vo) and np.array_equal(c1, co) and np.array_equal(n1, no)
     assert n1.min() < n1.max()  # iteration counts really diverge, so frames were handed over
     assert s1["kernel_launches"] > s0["kernel_launches"]
+
+
+@pytest.mark.parametrize("rounds,eighths,nf_later", [(3, 4, 1), (4, 4, 2), (3, 5, 2), (4, 6, 1), (2, 3, 2), (3, 2, 1)])
+def test_multi_round_compaction_is_transparent(oracle, rounds, eighths, nf_later):
+    """Any number of rounds, hand-over threshold and later-round group width gives the oracle's bits, CWD and counts
+    (frames handed over twice or three times find their way back to their own bit lane)."""
+    modcod, F = "QPSK-S_8/9", 1100
+    if "mr" not in _CACHE:
+        Y, _ = _llrs(oracle, modcod, F, 4.0, seed=91)
+        _CACHE["mr"] = (Y,) + tuple(oracle.ldpc_decode(MODCODS[modcod]["N_bch"], Y))
+    Y, Vo, co, no = _CACHE["mr"]
+    V, c, n, st = _decode(modcod, Y, compaction_rounds=rounds, compaction_exit_eighths=eighths, compaction_nf_later=nf_later)
+    assert np.array_equal(n, no) and np.array_equal(c, co) and np.array_equal(V, Vo)
+    assert st["frames"] == F and st["ldpc_iterations"] == int(no.sum()) and st["ldpc_failures"] == int((co == 0).sum())
+    assert st["kernel_launches"] >= 1 + 4 * (rounds - 1)
+
+
+@pytest.mark.parametrize("prec,modcod,ebn0", [("i16", "8PSK-S_3/5", 4.0), ("i8", "QPSK-S_8/9", 4.0)])
+def test_multi_round_compaction_fixed_point(oracle, prec, modcod, ebn0):
+    F = 700
+    Y, _ = _llrs(oracle, modcod, F, ebn0, seed=92)
+    Y = oracle.quantize(Y, 1 if prec == "i8" else 2, 6, prec)
+    from dvbs2_b200 import Decoder_LDPC_DVBS2_cuda, Handle
+
+    h = Handle(modcod=modcod, precision=prec, quant_dec=1 if prec == "i8" else 2, n_frames=F, compaction_rounds=3)
+    dec = Decoder_LDPC_DVBS2_cuda(h, F)
+    V, cwd, nit = np.zeros((F, dec.K), np.int32), np.zeros(F, np.int8), np.zeros(F, np.int32)
+    dec.decode_siho(Y, cwd, V, nit)
+    h.close()
+    Vo, co, no = oracle.ldpc_decode(MODCODS[modcod]["N_bch"], Y, prec=prec)
+    assert np.array_equal(nit, no) and np.array_equal(cwd, co) and np.array_equal(V, Vo)
 
 
 def _decode_i8(modcod, Y, compaction):
