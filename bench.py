@@ -47,8 +47,8 @@ def parse():
     p.add_argument("--ebn0", type=float, default=None)
     p.add_argument("--prec", default="f32", choices=["f32", "i16", "i8"])
     p.add_argument("--ite", type=int, default=10)
-    p.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: SMs x 12 warps x 64 frames = one full wave of the LDPC kernel)")
-    p.add_argument("--e2e-frames", type=int, default=1 << 30, help="frames per e2e step per GPU (default: same as --frames)")
+    p.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the largest of 3, 2, 1 waves of the LDPC kernel = SMs x 12 warps x 64 frames each that fits in 70 %% of the free HBM)")
+    p.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e step per GPU (default: one wave)")
     p.add_argument("--e2e-clones", type=int, default=3)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
@@ -227,8 +227,17 @@ def main():
     K_bch, N_bch, bps = mc["K_bch"], mc["N_bch"], mc["bps"]
     n_sym = N_LDPC // bps
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    F = args.frames if args.frames > 0 else sms * 12 * 64
     NB = 2  # input batches rotated between steps (each is far larger than the 126 MB L2)
+    wave = sms * 12 * 64  # frames one launch of the LDPC kernel holds in flight (12 warps per SM, 64 frames per warp)
+    if args.frames > 0:
+        F = args.frames
+    else:
+        # several waves per launch let the work queue balance groups that stop at different iterations (measured:
+        # 17.4 / 18.3 / 19.2 Gbit/s at 1 / 2 / 3 waves, profiles/README.md); bounded by what fits in HBM beside the inputs
+        esz0 = {"f32": 4, "i16": 2, "i8": 1}[args.prec]
+        per_frame = 1.6 * (N_LDPC * esz0 + (N_LDPC - N_bch) * 16 + N_LDPC // 4) + NB * (2 * n_sym * 4 + 4) + K_bch * 4 + 16
+        free_b = torch.cuda.mem_get_info(dev)[0]
+        F = next((k * wave for k in (3, 2) if k * wave * per_frame < 0.7 * free_b), wave)
 
     tune = dict(compaction=not args.no_compaction, compaction_rounds=args.rounds, compaction_exit_eighths=args.exit_eighths,
                 compaction_nf_later=args.nf_later)
@@ -328,7 +337,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         NC = max(1, args.e2e_clones)
-        Fe = max(256, min(F, args.e2e_frames) // NC // 256 * 256)
+        Fe = max(256, min(F, args.e2e_frames if args.e2e_frames > 0 else wave) // NC // 256 * 256)
         clones = []
         for c in range(NC):
             hc = Handle(modcod=modcod, n_ite=args.ite, norm=1.0, precision=args.prec, early_stop=True, n_frames=Fe, device=local,
@@ -338,16 +347,21 @@ def main():
             hV = torch.empty((Fe, K_bch), dtype=torch.int32).pin_memory()
             hc1, hc2 = torch.empty(Fe, dtype=torch.int8).pin_memory(), torch.empty(Fe, dtype=torch.int8).pin_memory()
             hn = torch.empty(Fe, dtype=torch.int32).pin_memory()
+            hP = torch.empty((Fe, K_bch // 8), dtype=torch.uint8).pin_memory()
             hs.copy_(batches[0][0][c * Fe:(c + 1) * Fe])
             hx.copy_(batches[0][1][c * Fe:(c + 1) * Fe])
-            clones.append((hc, Decoder_chain_DVBS2_cuda(hc, Fe), [t.numpy() for t in (hs, hx, hc1, hc2, hV, hn)], (hs, hx, hV, hc1, hc2, hn)))
+            clones.append((hc, Decoder_chain_DVBS2_cuda(hc, Fe), [t.numpy() for t in (hs, hx, hc1, hc2, hV, hn)],
+                           (hs, hx, hV, hc1, hc2, hn, hP)))
         torch.cuda.synchronize()
 
-        def run_clones(n):
+        def run_clones(n, packed=False):
             def work(c):
-                _, che, a, _ = clones[c]
+                _, che, a, keep = clones[c]
                 for _ in range(n):
-                    che.demodulate_decode(*a)
+                    if packed:  # bit-packed, descrambled payload bytes out instead of int32 per bit
+                        che.demodulate_decode_packed(a[0], a[1], a[2], a[3], keep[6].numpy(), a[5], descramble=True)
+                    else:
+                        che.demodulate_decode(*a)
             ths = [threading.Thread(target=work, args=(c,)) for c in range(NC)]
             for t in ths:
                 t.start()
@@ -376,6 +390,20 @@ def main():
                "clones": NC, "ms_per_step": round(w / args.steps * 1e3, 3), "gpu_launches": int(e2e_launches),
                "matches_device_path": same,
                "api": "dvbs2_cuda_chain (host pointers, pinned), %d concurrent module clones x %d frames" % (NC, Fe)}
+        # the same stage with the bit-packed output format (1/32 of the D2H bytes); not the headline: other socket types
+        run_clones(1, packed=True)
+        barrier()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        run_clones(args.steps, packed=True)
+        torch.cuda.synchronize()
+        wp = time.perf_counter() - w0
+        wp = reduce_([wp], dist.ReduceOp.MAX if world > 1 else None)[0]
+        barrier()
+        e2e["packed_output"] = {"value": round(K_bch * Fe * NC * args.steps * world / wp / 1e6, 2), "unit": "Mbit/s",
+                                "d2h_bytes_per_step": int(NC * (Fe * (K_bch // 8) + 2 * Fe + Fe * 4)),
+                                "ms_per_step": round(wp / args.steps * 1e3, 3),
+                                "api": "dvbs2_cuda_chain_packed (descrambled payload, 8 bits per byte)"}
         for hc, _, _, _ in clones:
             hc.close()
         del clones

@@ -23,7 +23,7 @@ SYMBOLS = [
     "dvbs2_cuda_stream", "dvbs2_cuda_sync", "dvbs2_cuda_demodulate_dev", "dvbs2_cuda_ldpc_decode_siho_dev",
     "dvbs2_cuda_bch_decode_hiho_dev", "dvbs2_cuda_chain_dev", "dvbs2_cuda_set_profiling", "dvbs2_cuda_get_timers",
     "dvbs2_cuda_tx_set_payload", "dvbs2_cuda_tx_random_payload", "dvbs2_cuda_tx_modulate_awgn_dev", "dvbs2_cuda_tx_get_bits",
-    "dvbs2_cuda_monitor_check", "dvbs2_cuda_monitor_get",
+    "dvbs2_cuda_monitor_check", "dvbs2_cuda_monitor_get", "dvbs2_cuda_chain_packed", "dvbs2_cuda_chain_packed_dev",
 ]
 
 
@@ -101,6 +101,8 @@ def load():
     L.dvbs2_cuda_ldpc_decode_siho_dev.argtypes = [vp, vp, vp, vp, vp, ip]
     L.dvbs2_cuda_bch_decode_hiho_dev.argtypes = [vp, vp, vp, vp, ip]
     L.dvbs2_cuda_chain_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, ip]
+    L.dvbs2_cuda_chain_packed.argtypes = [vp, vp, vp, vp, vp, vp, vp, ip, ip]
+    L.dvbs2_cuda_chain_packed_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, ip, ip]
     L.dvbs2_cuda_tx_set_payload.argtypes = [vp, vp, ip]
     L.dvbs2_cuda_tx_random_payload.argtypes = [vp, C.c_uint64, ip]
     L.dvbs2_cuda_tx_modulate_awgn_dev.argtypes = [vp, C.c_float, C.c_uint64, vp, vp, ip]

@@ -69,6 +69,7 @@ struct dvbs2_cuda_handle
     uint16_t* d_alpha_to = nullptr;
     int16_t* d_index_of = nullptr;
     float* d_cstl = nullptr;
+    uint8_t* d_scr_bytes = nullptr; // BB scrambler sequence, 8 bits per byte, LSB first
     BchDevTables bch{};
     // decoder state
     DevBuf var, cn, hd, out_hd, rem, nz, cwd_ldpc, cwd_bch, nit, stats;
@@ -78,6 +79,7 @@ struct dvbs2_cuda_handle
     DevBuf surv_mask, surv_iters, dst_base, src_of_dst, slot_frame, slot_iters, final_loc, n_surv;
     int ext_cap = 0, ext_slots = 0;
     int rounds = 1;       // decoding rounds (1 = no compaction)
+    bool auto_rounds = false; // rounds chosen per call from the batch size (cfg.compaction_rounds == 0)
     int exit_eighths = 4; // a group hands its live frames over once fewer than exit_eighths/8 of its frames still iterate
     int nf_later = 1;     // frames per lane in rounds >= 2
     // staging for the host-buffer entry points (grown on demand, never beyond max_frames)
@@ -290,7 +292,10 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
     size_t prev_hs = (size_t)first_frame; // slot-space index of prev's slot 0
     const int* prev_frame = nullptr;
     const int* prev_n_slots = nullptr;
-    for (int r = 2; r <= h->rounds && prev.n_groups >= 2; r++)
+    // measured (profiles/README.md): a third round pays once a launch holds two or more waves of groups (the queue then
+    // has work to balance); with a single wave the extra compaction and the short tail kernel cost more than they save
+    const int rounds = (h->auto_rounds && n_groups0 < 2 * h->n_sms * LDPC_WARPS) ? 2 : h->rounds;
+    for (int r = 2; r <= rounds && prev.n_groups >= 2; r++)
     {
         const int nf = ldpc_later_frames_per_lane(h->cfg.precision, h->nf_later);
         const int gsz = 32 * nf;
@@ -324,7 +329,7 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
         b.queue = h->d_queue + 8 * (r - 1) + slot;
         b.n_frames = cap, b.n_groups = cap / gsz, b.nf = nf;
         b.n_slots_dev = c.n_surv, b.slot_frame = c.dst_frame, b.slot_iters = c.dst_iters;
-        const bool last = r == h->rounds || b.n_groups < 2;
+        const bool last = r == rounds || b.n_groups < 2;
         b.exit_below = last ? 0 : gsz * h->exit_eighths / 8;
         b.surv_mask = last ? nullptr : (uint32_t*)h->surv_mask.p + hs / 32;
         b.surv_iters = last ? nullptr : (int*)h->surv_iters.p + hs;
@@ -378,7 +383,8 @@ run_bch(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const int32_t* d_
 
 int
 run_chain(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const float* d_sigma, const float* d_sym,
-          int8_t* d_cwd_ldpc, int8_t* d_cwd_bch, int32_t* d_VK, int32_t* d_nit, int n_frames)
+          int8_t* d_cwd_ldpc, int8_t* d_cwd_bch, int32_t* d_VK, int32_t* d_nit, int n_frames, uint8_t* d_packed = nullptr,
+          int descramble = 0)
 {
     if (n_frames == 0) return DVBS2_OK;
     void* var = (char*)h->var.p + (size_t)first_frame * N_LDPC * h->elt;
@@ -389,7 +395,11 @@ run_chain(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const float* d_
     TRY(prof_mark(h, s, P_BCH));
     CU(h, launch_bch_decode(bch_args(h, first_frame, n_frames, d_cwd_bch), h->bch, s));
     TRY(prof_mark(h, s, P_UNPACK));
-    CU(h, launch_unpack_bits((uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC, d_VK, N_LDPC, h->mc.K_bch, n_frames, s));
+    const uint32_t* words = (uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC;
+    if (d_packed)
+        CU(h, launch_unpack_bytes(words, descramble ? h->d_scr_bytes : nullptr, d_packed, N_LDPC, h->mc.K_bch, n_frames, s));
+    else
+        CU(h, launch_unpack_bits(words, d_VK, N_LDPC, h->mc.K_bch, n_frames, s));
     TRY(prof_mark(h, s, P_END));
     h->launches += 4;
     return DVBS2_OK;
@@ -507,7 +517,7 @@ extern "C"
                            &h->tx_gmask, &h->mon })
             if (b->p) cudaFree(b->p);
         for (void* p : { (void*)h->d_idx, (void*)h->d_idx32, (void*)h->d_last, (void*)h->d_queue, (void*)h->d_alpha_to,
-                         (void*)h->d_index_of, (void*)h->d_cstl })
+                         (void*)h->d_index_of, (void*)h->d_cstl, (void*)h->d_scr_bytes })
             if (p) cudaFree(p);
         for (int i = 0; i < N_PIPE; i++)
         {
@@ -602,6 +612,14 @@ extern "C"
         CUB(cudaMemcpy(h->d_index_of, bt.index_of.data(), bt.index_of.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
         CUB(cudaMalloc(&h->d_cstl, cstl.size() * sizeof(float)));
         CUB(cudaMemcpy(h->d_cstl, cstl.data(), cstl.size() * sizeof(float), cudaMemcpyHostToDevice));
+        {
+            std::vector<uint8_t> sb(mc.K_bch / 8, 0);
+            const std::vector<uint8_t> bits = build_bb_scrambler(mc.K_bch);
+            for (int i = 0; i < mc.K_bch; i++)
+                sb[i / 8] |= (uint8_t)((bits[i] & 1) << (i % 8));
+            CUB(cudaMalloc(&h->d_scr_bytes, sb.size()));
+            CUB(cudaMemcpy(h->d_scr_bytes, sb.data(), sb.size(), cudaMemcpyHostToDevice));
+        }
         h->bch.alpha_to = h->d_alpha_to, h->bch.index_of = h->d_index_of;
         memcpy(h->bch.minpoly, bt.minpoly, sizeof(bt.minpoly));
         memcpy(h->bch.poly_of, bt.poly_of, sizeof(bt.poly_of));
@@ -609,7 +627,8 @@ extern "C"
 
         const size_t G = (size_t)h->max_groups, F = (size_t)h->max_frames;
         // multi-round decoding: rounds / hand-over threshold / later-round group width (0 = defaults)
-        h->rounds = cfg->no_compaction ? 1 : (cfg->compaction_rounds > 0 ? std::min(cfg->compaction_rounds, 4) : 2);
+        h->rounds = cfg->no_compaction ? 1 : (cfg->compaction_rounds > 0 ? std::min(cfg->compaction_rounds, 4) : 3);
+        h->auto_rounds = !cfg->no_compaction && cfg->compaction_rounds <= 0;
         h->exit_eighths = cfg->compaction_exit_eighths > 0 ? std::min(cfg->compaction_exit_eighths, 6) : 4;
         h->nf_later = ldpc_later_frames_per_lane(cfg->precision, cfg->compaction_nf_later);
         h->ext_cap = h->rounds > 1 ? (int)region_b_offset(h, (h->max_frames + 255) / 256 * 256) + 512 : 0;
@@ -756,6 +775,16 @@ extern "C"
         return run_chain(h, h->stream, 0, d_CP, d_Y_N1, d_CWD_ldpc, d_CWD_bch, d_V_K, d_n_iter, n_frames);
     }
 
+    int dvbs2_cuda_chain_packed_dev(dvbs2_cuda_handle* h, const float* d_CP, const float* d_Y_N1, int8_t* d_CWD_ldpc,
+                                    int8_t* d_CWD_bch, uint8_t* d_V_K_packed, int32_t* d_n_iter, int descramble, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!d_CP || !d_Y_N1 || !d_V_K_packed) return DVBS2_ERR_INVALID;
+        CU(h, cudaSetDevice(h->cfg.device));
+        return run_chain(h, h->stream, 0, d_CP, d_Y_N1, d_CWD_ldpc, d_CWD_bch, nullptr, d_n_iter, n_frames, d_V_K_packed,
+                         descramble);
+    }
+
     // ------------------------------------------------------------------------------------------ host-pointer API
     int dvbs2_cuda_demodulate(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, float* Y_N2, int n_frames)
     {
@@ -871,18 +900,21 @@ extern "C"
         return DVBS2_OK;
     }
 
-    int dvbs2_cuda_chain(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
-                         int32_t* V_K, int32_t* n_iter, int n_frames)
+    // V_K: int32 per bit (AFF3CT socket type) when packed == nullptr, else packed bytes
+    static int chain_host(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
+                          int32_t* V_K, uint8_t* packed, int descramble, int32_t* n_iter, int n_frames)
     {
         TRY(check_frames(h, n_frames));
-        if (!CP || !Y_N1 || !V_K) return DVBS2_ERR_INVALID;
+        if (!CP || !Y_N1 || (!V_K && !packed)) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
-        const size_t inf = (size_t)2 * h->mc.n_sym * sizeof(float), outf = (size_t)h->mc.K_bch * sizeof(int32_t);
+        const size_t inf = (size_t)2 * h->mc.n_sym * sizeof(float);
+        const size_t outf = packed ? (size_t)h->mc.K_bch / 8 : (size_t)h->mc.K_bch * sizeof(int32_t);
         TRY(ensure(h, h->in_a, inf * n_frames));
         TRY(ensure(h, h->out_a, outf * n_frames));
         TRY(ensure(h, h->sigma, sizeof(float) * n_frames));
         const int per = chunk_frames(h, n_frames);
+        char* const host_out = packed ? (char*)packed : (char*)V_K;
         int ci = 0;
         for (int f0 = 0; f0 < n_frames; f0 += per, ci++)
         {
@@ -890,14 +922,15 @@ extern "C"
             cudaStream_t s = h->pipe[ci % N_PIPE];
             float* d_sym = (float*)((char*)h->in_a.p + inf * f0);
             float* d_sig = (float*)h->sigma.p + f0;
-            int32_t* d_out = (int32_t*)((char*)h->out_a.p + outf * f0);
+            char* d_out = (char*)h->out_a.p + outf * f0;
             int8_t* d_c1 = (int8_t*)h->cwd_ldpc.p + f0;
             int8_t* d_c2 = (int8_t*)h->cwd_bch.p + f0;
             int32_t* d_nit = (int32_t*)h->nit.p + f0;
             CU(h, cudaMemcpyAsync(d_sig, CP + f0, sizeof(float) * nf, cudaMemcpyHostToDevice, s));
             CU(h, cudaMemcpyAsync(d_sym, (const char*)Y_N1 + inf * f0, inf * nf, cudaMemcpyHostToDevice, s));
-            TRY(run_chain(h, s, f0, d_sig, d_sym, d_c1, d_c2, d_out, d_nit, nf));
-            CU(h, cudaMemcpyAsync((char*)V_K + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
+            TRY(run_chain(h, s, f0, d_sig, d_sym, d_c1, d_c2, packed ? nullptr : (int32_t*)d_out, d_nit, nf,
+                          packed ? (uint8_t*)d_out : nullptr, descramble));
+            CU(h, cudaMemcpyAsync(host_out + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
             if (CWD_ldpc) CU(h, cudaMemcpyAsync(CWD_ldpc + f0, d_c1, nf, cudaMemcpyDeviceToHost, s));
             if (CWD_bch) CU(h, cudaMemcpyAsync(CWD_bch + f0, d_c2, nf, cudaMemcpyDeviceToHost, s));
             if (n_iter) CU(h, cudaMemcpyAsync(n_iter + f0, d_nit, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, s));
@@ -905,6 +938,20 @@ extern "C"
         for (int i = 0; i < N_PIPE; i++)
             CU(h, cudaStreamSynchronize(h->pipe[i]));
         return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_chain(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
+                         int32_t* V_K, int32_t* n_iter, int n_frames)
+    {
+        if (!V_K) return DVBS2_ERR_INVALID;
+        return chain_host(h, CP, Y_N1, CWD_ldpc, CWD_bch, V_K, nullptr, 0, n_iter, n_frames);
+    }
+
+    int dvbs2_cuda_chain_packed(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
+                                uint8_t* V_K_packed, int32_t* n_iter, int descramble, int n_frames)
+    {
+        if (!V_K_packed) return DVBS2_ERR_INVALID;
+        return chain_host(h, CP, Y_N1, CWD_ldpc, CWD_bch, nullptr, V_K_packed, descramble, n_iter, n_frames);
     }
 
     // ------------------------------------------------------------------------------- transmitter / channel / monitor

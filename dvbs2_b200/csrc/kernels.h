@@ -95,6 +95,8 @@ int ldpc_frames_per_lane(int precision); // NF: 2 (f32, i16), 4 (i8)
 cudaError_t launch_ldpc_decode(const LdpcLaunch& a, int precision, cudaStream_t s);
 cudaError_t launch_pack_llr(const void* in, void* var, int precision, int n_frames, cudaStream_t s);
 cudaError_t launch_unpack_bits(const uint32_t* words, int32_t* out, int stride, int K, int n_frames, cudaStream_t s);
+cudaError_t launch_unpack_bytes(const uint32_t* words, const uint8_t* scr, uint8_t* out, int stride, int K, int n_frames,
+                                cudaStream_t s);
 cudaError_t launch_pack_bits(const int32_t* in, uint32_t* words, int stride, int N, int n_frames, cudaStream_t s);
 
 struct DemapLaunch

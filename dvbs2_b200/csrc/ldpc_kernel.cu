@@ -668,6 +668,33 @@ unpack_bits_kernel(const uint32_t* __restrict__ words, int32_t* __restrict__ out
     }
 }
 
+// bit-sliced words [subgroup][stride] -> packed bytes [F][K/8], bit i of a frame at byte i/8, bit i%8 (the layout of
+// spu::tools::Bit_packer::pack with msb_to_lsb = false, lib/streampu/include/Tools/Algo/Bit_packer/Bit_packer.hxx, which
+// Sink_user_binary writes to disk); scr (or null) = the BB scrambler sequence packed the same way, XORed in
+// (Scrambler_BB::descramble, src/common/Module/Scrambler/Scrambler_BB/Scrambler_BB.hxx:51-72).  thread = (subgroup, byte).
+__global__ void
+unpack_bytes_kernel(const uint32_t* __restrict__ words, const uint8_t* __restrict__ scr, uint8_t* __restrict__ out, int stride,
+                    int KB, int n_frames)
+{
+    const int g = blockIdx.y;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= KB) return;
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        w[k] = words[(size_t)g * stride + 8 * b + k];
+    const uint32_t x = scr ? scr[b] : 0u;
+    const int nf = min(32, n_frames - g * 32);
+    for (int f = 0; f < nf; f++)
+    {
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            v |= ((w[k] >> f) & 1u) << k;
+        out[(size_t)(g * 32 + f) * KB + b] = (uint8_t)(v ^ x);
+    }
+}
+
 // int32 bits [F][N] -> bit-sliced words [subgroup][stride]
 __global__ void
 pack_bits_kernel(const int32_t* __restrict__ in, uint32_t* __restrict__ words, int stride, int N, int n_frames)
@@ -806,6 +833,16 @@ launch_unpack_bits(const uint32_t* words, int32_t* out, int stride, int K, int n
     const int groups = (n_frames + 31) / 32;
     const dim3 grid((K + 127) / 128, groups);
     unpack_bits_kernel<<<grid, 128, 0, s>>>(words, out, stride, K, n_frames);
+    return cudaGetLastError();
+}
+
+cudaError_t
+launch_unpack_bytes(const uint32_t* words, const uint8_t* scr, uint8_t* out, int stride, int K, int n_frames, cudaStream_t s)
+{
+    if (K % 8) return cudaErrorInvalidValue;
+    const int groups = (n_frames + 31) / 32;
+    const dim3 grid((K / 8 + 127) / 128, groups);
+    unpack_bytes_kernel<<<grid, 128, 0, s>>>(words, scr, out, stride, K / 8, n_frames);
     return cudaGetLastError();
 }
 

@@ -34,7 +34,8 @@ def _np_ptr(a, dtype, n_elem, name):
 def _dev_ptr(t, dtype_name, n_elem, name):
     import torch
 
-    want = {"float32": torch.float32, "int32": torch.int32, "int16": torch.int16, "int8": torch.int8}[dtype_name]
+    want = {"float32": torch.float32, "int32": torch.int32, "int16": torch.int16, "int8": torch.int8,
+            "uint8": torch.uint8}[dtype_name]
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == want and t.is_contiguous()):
         raise ValueError("'%s' must be a contiguous CUDA tensor of %s" % (name, dtype_name))
     if t.numel() != n_elem:
@@ -234,6 +235,26 @@ class Decoder_chain_DVBS2_cuda(_Module):
             None if CWD_bch is None else _dev_ptr(CWD_bch, "int8", F, "CWD_bch"),
             _dev_ptr(V_K, "int32", F * self.K, "V_K"),
             None if n_iter is None else _dev_ptr(n_iter, "int32", F, "n_iter"), F))
+
+
+    def demodulate_decode_packed(self, CP, Y_N1, CWD_ldpc, CWD_bch, V_K_packed, n_iter=None, descramble=False):
+        """Same stage, bit-packed output [F][K_bch/8] uint8 (Bit_packer layout, LSB first), optionally BB-descrambled."""
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_chain_packed(
+            h._h, _np_ptr(CP, np.float32, F, "CP"), _np_ptr(Y_N1, np.float32, F * self.N_fil, "Y_N1"),
+            None if CWD_ldpc is None else _np_ptr(CWD_ldpc, np.int8, F, "CWD_ldpc"),
+            None if CWD_bch is None else _np_ptr(CWD_bch, np.int8, F, "CWD_bch"),
+            _np_ptr(V_K_packed, np.uint8, F * (self.K // 8), "V_K_packed"),
+            None if n_iter is None else _np_ptr(n_iter, np.int32, F, "n_iter"), int(bool(descramble)), F))
+
+    def demodulate_decode_packed_dev(self, CP, Y_N1, CWD_ldpc, CWD_bch, V_K_packed, n_iter=None, descramble=False):
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_chain_packed_dev(
+            h._h, _dev_ptr(CP, "float32", F, "CP"), _dev_ptr(Y_N1, "float32", F * self.N_fil, "Y_N1"),
+            None if CWD_ldpc is None else _dev_ptr(CWD_ldpc, "int8", F, "CWD_ldpc"),
+            None if CWD_bch is None else _dev_ptr(CWD_bch, "int8", F, "CWD_bch"),
+            _dev_ptr(V_K_packed, "uint8", F * (self.K // 8), "V_K_packed"),
+            None if n_iter is None else _dev_ptr(n_iter, "int32", F, "n_iter"), int(bool(descramble)), F))
 
 
 class Transmitter_DVBS2_cuda(_Module):

@@ -146,6 +146,15 @@ extern "C"
     int dvbs2_cuda_chain(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
                          int32_t* V_K, int32_t* n_iter, int n_frames);
 
+    /* The same stage with the bit-packed output format: V_K_packed[F][K_bch/8] bytes, bit i of a frame at
+     * byte i/8, bit i%8 — the layout of spu::tools::Bit_packer::pack(msb_to_lsb = false) that Sink_user_binary writes
+     * (lib/streampu/src/Module/Stateful/Sink/User/Sink_user_binary.cpp:70-77) — 32x fewer D2H bytes than int32 per bit.
+     * descramble != 0 also applies Scrambler_BB::descramble (src/common/Module/Scrambler/Scrambler_BB/Scrambler_BB.hxx:51-72),
+     * the task bound behind decode_hiho in src/mains/TX_RX_BB/main.cpp:92 and src/mains/RX/main_sched.cpp:211, so the bytes
+     * are the payload the sink stores. */
+    int dvbs2_cuda_chain_packed(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
+                                uint8_t* V_K_packed, int32_t* n_iter, int descramble, int n_frames);
+
     /* pin / unpin a caller-owned host buffer (StreamPU socket buffers are stable after binding) */
     int dvbs2_cuda_host_register(dvbs2_cuda_handle* h, void* ptr, size_t bytes);
     int dvbs2_cuda_host_unregister(dvbs2_cuda_handle* h, void* ptr);
@@ -161,6 +170,9 @@ extern "C"
                                        int n_frames);
     int dvbs2_cuda_chain_dev(dvbs2_cuda_handle* h, const float* d_CP, const float* d_Y_N1, int8_t* d_CWD_ldpc,
                              int8_t* d_CWD_bch, int32_t* d_V_K, int32_t* d_n_iter, int n_frames);
+
+    int dvbs2_cuda_chain_packed_dev(dvbs2_cuda_handle* h, const float* d_CP, const float* d_Y_N1, int8_t* d_CWD_ldpc,
+                                    int8_t* d_CWD_bch, uint8_t* d_V_K_packed, int32_t* d_n_iter, int descramble, int n_frames);
 
     /* ---- on-device transmitter, AWGN channel and BER/FER monitor ------------------------------------------------
      * Monte-Carlo / benchmark harness around the decode path: what D/mains/TX_RX_BB/main.cpp:75-84

@@ -187,6 +187,39 @@ def test_device_resident_api_matches_host_api(oracle):
     h.close()
 
 
+@pytest.mark.parametrize("modcod,ebn0,F", [("QPSK-S_8/9", 4.0, 70), ("8PSK-S_3/5", 4.0, 33)])
+def test_packed_output_format(oracle, modcod, ebn0, F):
+    """SURVEY §8f N2: the bit-packed socket format is the int32 output packed like spu::tools::Bit_packer (LSB first), and
+    with descramble it is the packed Scrambler_BB::descramble output; host and device entry points agree."""
+    import torch
+
+    from dvbs2_b200 import Decoder_chain_DVBS2_cuda, Handle
+
+    mc = MODCODS[modcod]
+    K = mc["K_bch"]
+    s = synth_frames(oracle, modcod, F, ebn0, seed=53)
+    h = Handle(modcod=modcod, n_frames=F)
+    ch = Decoder_chain_DVBS2_cuda(h, F)
+    V = np.zeros((F, K), np.int32)
+    c1, c2, nit = np.zeros(F, np.int8), np.zeros(F, np.int8), np.zeros(F, np.int32)
+    ch.demodulate_decode(s["sigma"], s["rx"], c1, c2, V, nit)
+    for descramble in (False, True):
+        P = np.zeros((F, K // 8), np.uint8)
+        p1, p2, pn = np.zeros(F, np.int8), np.zeros(F, np.int8), np.zeros(F, np.int32)
+        ch.demodulate_decode_packed(s["sigma"], s["rx"], p1, p2, P, pn, descramble=descramble)
+        want = oracle.bb_scramble(K, V) if descramble else V
+        assert np.array_equal(P, np.packbits(want.astype(np.uint8), axis=1, bitorder="little"))
+        assert np.array_equal(p1, c1) and np.array_equal(p2, c2) and np.array_equal(pn, nit)
+        dev = torch.device("cuda:0")
+        d_sig, d_rx = torch.from_numpy(s["sigma"]).to(dev), torch.from_numpy(s["rx"]).to(dev)
+        dP = torch.zeros((F, K // 8), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        ch.demodulate_decode_packed_dev(d_sig, d_rx, None, None, dP, None, descramble=descramble)
+        h.sync()
+        assert np.array_equal(dP.cpu().numpy(), P)
+    h.close()
+
+
 def test_chain_full_size_round_trip(oracle):
     """BASELINE-size property test: 8192 frames through the chunked host API; every frame BCH accepts must descramble
     to its payload, and at 5 dB (well past the waterfall) every frame is accepted."""
