@@ -228,14 +228,15 @@ def main():
     n_sym = N_LDPC // bps
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     NB = 2  # input batches rotated between steps (each is far larger than the 126 MB L2)
-    wave = sms * 12 * 64  # frames one launch of the LDPC kernel holds in flight (12 warps per SM, 64 frames per warp)
+    # frames one launch of the LDPC kernel holds in flight: 12 warps per SM, 64 (f32) or 128 (i16, i8) frames per warp
+    wave = sms * 12 * (64 if args.prec == "f32" else 128)
     if args.frames > 0:
         F = args.frames
     else:
         # several waves per launch let the work queue balance groups that stop at different iterations (measured:
         # 17.4 / 18.3 / 19.2 Gbit/s at 1 / 2 / 3 waves, profiles/README.md); bounded by what fits in HBM beside the inputs
         esz0 = {"f32": 4, "i16": 2, "i8": 1}[args.prec]
-        per_frame = 1.6 * (N_LDPC * esz0 + (N_LDPC - N_bch) * 16 + N_LDPC // 4) + NB * (2 * n_sym * 4 + 4) + K_bch * 4 + 16
+        per_frame = 1.6 * (N_LDPC * esz0 + (N_LDPC - N_bch) * (8 if args.prec == "i16" else 16) + N_LDPC // 4) + NB * (2 * n_sym * 4 + 4) + K_bch * 4 + 16
         free_b = torch.cuda.mem_get_info(dev)[0]
         F = next((k * wave for k in (3, 2) if k * wave * per_frame < 0.7 * free_b), wave)
 
@@ -316,7 +317,8 @@ def main():
     d_info = 25 if N_bch == 14400 else 9
     E_info = M * d_info
     it_per_frame = st["ldpc_iterations"] / max(1, st["frames"])
-    msg_bytes_frame = it_per_frame * (2 * esz * E_info + 2 * esz * M + 32 * M)  # DESIGN.md §5 message-passing traffic
+    cn_rw = 16 if args.prec == "i16" else 32  # check state read + written per check and frame (packed pairs for int16)
+    msg_bytes_frame = it_per_frame * (2 * esz * E_info + 2 * esz * M + cn_rw * M)  # DESIGN.md §5 message-passing traffic
     roofline = {"bound": "hbm", "kernel": "ldpc_decode_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_frame": alg_bytes_frame, "kernel_ms": round(ldpc_ms, 4),

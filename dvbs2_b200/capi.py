@@ -24,6 +24,8 @@ SYMBOLS = [
     "dvbs2_cuda_bch_decode_hiho_dev", "dvbs2_cuda_chain_dev", "dvbs2_cuda_set_profiling", "dvbs2_cuda_get_timers",
     "dvbs2_cuda_tx_set_payload", "dvbs2_cuda_tx_random_payload", "dvbs2_cuda_tx_modulate_awgn_dev", "dvbs2_cuda_tx_get_bits",
     "dvbs2_cuda_monitor_check", "dvbs2_cuda_monitor_get", "dvbs2_cuda_chain_packed", "dvbs2_cuda_chain_packed_dev",
+    "dvbs2_cuda_pl_frame_size", "dvbs2_cuda_remove_plh", "dvbs2_cuda_remove_plh_dev", "dvbs2_cuda_estimate",
+    "dvbs2_cuda_estimate_dev", "dvbs2_cuda_rx_chain", "dvbs2_cuda_rx_chain_dev",
 ]
 
 
@@ -103,6 +105,13 @@ def load():
     L.dvbs2_cuda_chain_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, ip]
     L.dvbs2_cuda_chain_packed.argtypes = [vp, vp, vp, vp, vp, vp, vp, ip, ip]
     L.dvbs2_cuda_chain_packed_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, ip, ip]
+    L.dvbs2_cuda_pl_frame_size.argtypes = [vp]
+    L.dvbs2_cuda_remove_plh.argtypes = [vp, vp, vp, ip]
+    L.dvbs2_cuda_remove_plh_dev.argtypes = [vp, vp, vp, ip]
+    L.dvbs2_cuda_estimate.argtypes = [vp, vp, vp, vp, vp, ip]
+    L.dvbs2_cuda_estimate_dev.argtypes = [vp, vp, vp, vp, vp, ip]
+    L.dvbs2_cuda_rx_chain.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ip, vp, ip]
+    L.dvbs2_cuda_rx_chain_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ip, vp, ip]
     L.dvbs2_cuda_tx_set_payload.argtypes = [vp, vp, ip]
     L.dvbs2_cuda_tx_random_payload.argtypes = [vp, C.c_uint64, ip]
     L.dvbs2_cuda_tx_modulate_awgn_dev.argtypes = [vp, C.c_float, C.c_uint64, vp, vp, ip]

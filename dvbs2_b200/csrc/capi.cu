@@ -58,6 +58,7 @@ struct dvbs2_cuda_handle
     int nf = 1, n_sms = 148;             // frames per lane of the LDPC kernel (group = 32 * nf frames)
     int k8 = 0;
     size_t elt = 4; // sizeof(R)
+    int cn_div = 1; // check state: 16 / cn_div bytes per frame and check (int16 packs two frames into one uint4)
     cudaStream_t stream = nullptr;
     cudaStream_t pipe[N_PIPE] = {};
     cudaEvent_t pipe_done[N_PIPE] = {};
@@ -194,7 +195,7 @@ ldpc_args(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frames, i
 {
     LdpcLaunch a{};
     a.var = (char*)h->var.p + (size_t)first_frame * N_LDPC * h->elt;
-    a.cn = (uint4*)h->cn.p + (size_t)first_frame * h->mc.M;
+    a.cn = (uint4*)h->cn.p + (size_t)first_frame * h->mc.M / h->cn_div;
     a.hd = (uint32_t*)h->hd.p + (size_t)(first_frame / 32) * N_LDPC;
     a.out_hd = (uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC;
     a.idx32 = h->d_idx32, a.last = h->d_last;
@@ -230,9 +231,10 @@ bch_args(dvbs2_cuda_handle* h, int first_frame, int n_frames, int8_t* cwd)
 }
 
 DemapLaunch
-demap_args(dvbs2_cuda_handle* h, const float* d_sigma, const float* d_sym, int n_frames)
+demap_args(dvbs2_cuda_handle* h, const float* d_sigma, const float* d_sym, int n_frames, bool pl_frames = false)
 {
     DemapLaunch d{};
+    d.pl_sym = pl_frames ? pl_frame_symbols(h->mc.n_sym) : 0;
     d.sigma = d_sigma, d.sym = d_sym, d.cstl = h->d_cstl, d.n_frames = n_frames;
     d.bps = h->mc.bps, d.n_sym = h->mc.n_sym, d.itl_cols = h->mc.itl_cols, d.itl_rev = h->mc.itl_rev;
     d.quant_dec = h->cfg.quant_dec, d.quant_bits = h->cfg.quant_bits;
@@ -318,7 +320,7 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
         c.final_loc = final_loc;
         c.dst_slot0 = (int)(hs - first_frame);
         c.var_src = prev.var, c.var_dst = (char*)h->var.p + vslot * N_LDPC * h->elt;
-        c.cn_src = prev.cn, c.cn_dst = (uint4*)h->cn.p + vslot * h->mc.M;
+        c.cn_src = prev.cn, c.cn_dst = (uint4*)h->cn.p + vslot * h->mc.M / h->cn_div;
         c.n_groups = prev.n_groups, c.nf = prev.nf, c.cap = cap, c.M = h->mc.M, c.nf_dst = nf;
         CU(h, launch_compact(c, h->cfg.precision, s));
 
@@ -384,12 +386,18 @@ run_bch(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const int32_t* d_
 int
 run_chain(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const float* d_sigma, const float* d_sym,
           int8_t* d_cwd_ldpc, int8_t* d_cwd_bch, int32_t* d_VK, int32_t* d_nit, int n_frames, uint8_t* d_packed = nullptr,
-          int descramble = 0)
+          int descramble = 0, bool pl_frames = false, float* d_sigma_est = nullptr)
 {
     if (n_frames == 0) return DVBS2_OK;
     void* var = (char*)h->var.p + (size_t)first_frame * N_LDPC * h->elt;
     TRY(prof_mark(h, s, P_DEMAP));
-    CU(h, launch_demap_to_var(demap_args(h, d_sigma, d_sym, n_frames), var, h->cfg.precision, h->nf, s));
+    if (d_sigma_est)
+    { // Estimator_DVBS2 in front of the demapper: sigma per frame from the frame's own payload symbols
+        CU(h, launch_estimate(demap_args(h, nullptr, d_sym, n_frames, pl_frames), h->mc.K_bch, d_sigma_est, nullptr, nullptr, s));
+        d_sigma = d_sigma_est;
+        h->launches += 1;
+    }
+    CU(h, launch_demap_to_var(demap_args(h, d_sigma, d_sym, n_frames, pl_frames), var, h->cfg.precision, h->nf, s));
     TRY(prof_mark(h, s, P_LDPC));
     TRY(run_ldpc_core(h, s, first_frame, n_frames, d_cwd_ldpc, d_nit));
     TRY(prof_mark(h, s, P_BCH));
@@ -399,7 +407,7 @@ run_chain(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const float* d_
     if (d_packed)
         CU(h, launch_unpack_bytes(words, descramble ? h->d_scr_bytes : nullptr, d_packed, N_LDPC, h->mc.K_bch, n_frames, s));
     else
-        CU(h, launch_unpack_bits(words, d_VK, N_LDPC, h->mc.K_bch, n_frames, s));
+        CU(h, launch_unpack_bits(words, d_VK, N_LDPC, h->mc.K_bch, n_frames, s, descramble ? h->d_scr_bytes : nullptr));
     TRY(prof_mark(h, s, P_END));
     h->launches += 4;
     return DVBS2_OK;
@@ -560,6 +568,7 @@ extern "C"
         h->k8 = k8;
         h->elt = cfg->precision == DVBS2_PREC_F32 ? 4 : cfg->precision == DVBS2_PREC_I16 ? 2 : 1;
         h->nf = ldpc_frames_per_lane(cfg->precision);
+        h->cn_div = cfg->precision == DVBS2_PREC_I16 ? 2 : 1;
         h->max_frames = (cfg->max_frames + 32 * h->nf - 1) / (32 * h->nf) * (32 * h->nf);
         h->max_groups = h->max_frames / 32;
 
@@ -636,7 +645,7 @@ extern "C"
         const size_t FE = F + h->ext_cap;                    // var / cn slots
         const size_t FS = F + h->ext_slots, GS = FS / 32;    // hd / out_hd / bookkeeping slots
         int rc;
-        if ((rc = ensure(h, h->var, FE * N_LDPC * h->elt)) || (rc = ensure(h, h->cn, FE * mc.M * sizeof(uint4))) ||
+        if ((rc = ensure(h, h->var, FE * N_LDPC * h->elt)) || (rc = ensure(h, h->cn, FE * mc.M * sizeof(uint4) / h->cn_div)) ||
             (rc = ensure(h, h->hd, GS * N_LDPC * 4)) || (rc = ensure(h, h->out_hd, GS * N_LDPC * 4)) ||
             (rc = ensure(h, h->surv_mask, GS * 4 + 4)) || (rc = ensure(h, h->surv_iters, FS * 4 + 4)) ||
             (rc = ensure(h, h->dst_base, GS * 4 + 4)) || (rc = ensure(h, h->src_of_dst, FS * 4 + 4)) ||
@@ -901,14 +910,17 @@ extern "C"
     }
 
     // V_K: int32 per bit (AFF3CT socket type) when packed == nullptr, else packed bytes
+    // pl_frames: Y_N1 holds whole PL frames (Framer::remove_plh fused in).  CP == nullptr: sigma comes from the on-device
+    // Estimator_DVBS2 and is returned in SIG (optional).
     static int chain_host(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
-                          int32_t* V_K, uint8_t* packed, int descramble, int32_t* n_iter, int n_frames)
+                          int32_t* V_K, uint8_t* packed, int descramble, int32_t* n_iter, int n_frames, bool pl_frames = false,
+                          float* SIG = nullptr)
     {
         TRY(check_frames(h, n_frames));
-        if (!CP || !Y_N1 || (!V_K && !packed)) return DVBS2_ERR_INVALID;
+        if (!Y_N1 || (!V_K && !packed)) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
-        const size_t inf = (size_t)2 * h->mc.n_sym * sizeof(float);
+        const size_t inf = (size_t)2 * (pl_frames ? pl_frame_symbols(h->mc.n_sym) : h->mc.n_sym) * sizeof(float);
         const size_t outf = packed ? (size_t)h->mc.K_bch / 8 : (size_t)h->mc.K_bch * sizeof(int32_t);
         TRY(ensure(h, h->in_a, inf * n_frames));
         TRY(ensure(h, h->out_a, outf * n_frames));
@@ -926,10 +938,11 @@ extern "C"
             int8_t* d_c1 = (int8_t*)h->cwd_ldpc.p + f0;
             int8_t* d_c2 = (int8_t*)h->cwd_bch.p + f0;
             int32_t* d_nit = (int32_t*)h->nit.p + f0;
-            CU(h, cudaMemcpyAsync(d_sig, CP + f0, sizeof(float) * nf, cudaMemcpyHostToDevice, s));
+            if (CP) CU(h, cudaMemcpyAsync(d_sig, CP + f0, sizeof(float) * nf, cudaMemcpyHostToDevice, s));
             CU(h, cudaMemcpyAsync(d_sym, (const char*)Y_N1 + inf * f0, inf * nf, cudaMemcpyHostToDevice, s));
             TRY(run_chain(h, s, f0, d_sig, d_sym, d_c1, d_c2, packed ? nullptr : (int32_t*)d_out, d_nit, nf,
-                          packed ? (uint8_t*)d_out : nullptr, descramble));
+                          packed ? (uint8_t*)d_out : nullptr, descramble, pl_frames, CP ? nullptr : d_sig));
+            if (SIG) CU(h, cudaMemcpyAsync(SIG + f0, d_sig, sizeof(float) * nf, cudaMemcpyDeviceToHost, s));
             CU(h, cudaMemcpyAsync(host_out + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
             if (CWD_ldpc) CU(h, cudaMemcpyAsync(CWD_ldpc + f0, d_c1, nf, cudaMemcpyDeviceToHost, s));
             if (CWD_bch) CU(h, cudaMemcpyAsync(CWD_bch + f0, d_c2, nf, cudaMemcpyDeviceToHost, s));
@@ -943,15 +956,102 @@ extern "C"
     int dvbs2_cuda_chain(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
                          int32_t* V_K, int32_t* n_iter, int n_frames)
     {
-        if (!V_K) return DVBS2_ERR_INVALID;
+        if (!V_K || !CP) return DVBS2_ERR_INVALID;
         return chain_host(h, CP, Y_N1, CWD_ldpc, CWD_bch, V_K, nullptr, 0, n_iter, n_frames);
     }
 
     int dvbs2_cuda_chain_packed(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
                                 uint8_t* V_K_packed, int32_t* n_iter, int descramble, int n_frames)
     {
-        if (!V_K_packed) return DVBS2_ERR_INVALID;
+        if (!V_K_packed || !CP) return DVBS2_ERR_INVALID;
         return chain_host(h, CP, Y_N1, CWD_ldpc, CWD_bch, nullptr, V_K_packed, descramble, n_iter, n_frames);
+    }
+
+    // -------------------------------------------------------- receiver stage from PL frames
+    int dvbs2_cuda_pl_frame_size(const dvbs2_cuda_handle* h)
+    {
+        return h ? 2 * pl_frame_symbols(h->mc.n_sym) : DVBS2_ERR_INVALID;
+    }
+
+    int dvbs2_cuda_remove_plh(dvbs2_cuda_handle* h, const float* Y_N1, float* Y_N2, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!Y_N1 || !Y_N2) return DVBS2_ERR_INVALID;
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        const size_t inf = (size_t)2 * pl_frame_symbols(h->mc.n_sym) * sizeof(float), outf = (size_t)2 * h->mc.n_sym * sizeof(float);
+        TRY(ensure(h, h->in_a, inf * n_frames));
+        TRY(ensure(h, h->out_a, outf * n_frames));
+        cudaStream_t s = h->stream;
+        CU(h, cudaMemcpyAsync(h->in_a.p, Y_N1, inf * n_frames, cudaMemcpyHostToDevice, s));
+        CU(h, launch_remove_plh((const float*)h->in_a.p, (float*)h->out_a.p, h->mc.n_sym, n_frames, s));
+        h->launches += 1;
+        CU(h, cudaMemcpyAsync(Y_N2, h->out_a.p, outf * n_frames, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaStreamSynchronize(s));
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_remove_plh_dev(dvbs2_cuda_handle* h, const float* d_Y_N1, float* d_Y_N2, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!d_Y_N1 || !d_Y_N2) return DVBS2_ERR_INVALID;
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        CU(h, launch_remove_plh(d_Y_N1, d_Y_N2, h->mc.n_sym, n_frames, h->stream));
+        h->launches += 1;
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_estimate(dvbs2_cuda_handle* h, const float* X_N, float* SIG, float* Eb_N0, float* Es_N0, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!X_N || !SIG) return DVBS2_ERR_INVALID;
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        const size_t inf = (size_t)2 * h->mc.n_sym * sizeof(float);
+        TRY(ensure(h, h->in_a, inf * n_frames));
+        TRY(ensure(h, h->out_a, 3 * sizeof(float) * (size_t)n_frames));
+        cudaStream_t s = h->stream;
+        float* d_sig = (float*)h->out_a.p;
+        float *d_eb = d_sig + n_frames, *d_es = d_sig + 2 * (size_t)n_frames;
+        CU(h, cudaMemcpyAsync(h->in_a.p, X_N, inf * n_frames, cudaMemcpyHostToDevice, s));
+        CU(h, launch_estimate(demap_args(h, nullptr, (const float*)h->in_a.p, n_frames), h->mc.K_bch, d_sig, d_eb, d_es, s));
+        h->launches += 1;
+        CU(h, cudaMemcpyAsync(SIG, d_sig, sizeof(float) * n_frames, cudaMemcpyDeviceToHost, s));
+        if (Eb_N0) CU(h, cudaMemcpyAsync(Eb_N0, d_eb, sizeof(float) * n_frames, cudaMemcpyDeviceToHost, s));
+        if (Es_N0) CU(h, cudaMemcpyAsync(Es_N0, d_es, sizeof(float) * n_frames, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaStreamSynchronize(s));
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_estimate_dev(dvbs2_cuda_handle* h, const float* d_X_N, float* d_SIG, float* d_Eb_N0, float* d_Es_N0,
+                                int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!d_X_N || !d_SIG) return DVBS2_ERR_INVALID;
+        if (n_frames == 0) return DVBS2_OK;
+        CU(h, cudaSetDevice(h->cfg.device));
+        CU(h, launch_estimate(demap_args(h, nullptr, d_X_N, n_frames), h->mc.K_bch, d_SIG, d_Eb_N0, d_Es_N0, h->stream));
+        h->launches += 1;
+        return DVBS2_OK;
+    }
+
+    int dvbs2_cuda_rx_chain(dvbs2_cuda_handle* h, const float* PL_frames, const float* CP, float* SIG, int8_t* CWD_ldpc,
+                            int8_t* CWD_bch, int32_t* V_K, uint8_t* V_K_packed, int descramble, int32_t* n_iter, int n_frames)
+    {
+        if ((V_K != nullptr) == (V_K_packed != nullptr)) return DVBS2_ERR_INVALID; // exactly one output format
+        return chain_host(h, CP, PL_frames, CWD_ldpc, CWD_bch, V_K, V_K_packed, descramble, n_iter, n_frames, true, SIG);
+    }
+
+    int dvbs2_cuda_rx_chain_dev(dvbs2_cuda_handle* h, const float* d_PL_frames, const float* d_CP, float* d_SIG,
+                                int8_t* d_CWD_ldpc, int8_t* d_CWD_bch, int32_t* d_V_K, uint8_t* d_V_K_packed, int descramble,
+                                int32_t* d_n_iter, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!d_PL_frames || (d_V_K != nullptr) == (d_V_K_packed != nullptr) || (!d_CP && !d_SIG)) return DVBS2_ERR_INVALID;
+        CU(h, cudaSetDevice(h->cfg.device));
+        return run_chain(h, h->stream, 0, d_CP, d_PL_frames, d_CWD_ldpc, d_CWD_bch, d_V_K, d_n_iter, n_frames, d_V_K_packed,
+                         descramble, true, d_CP ? nullptr : d_SIG);
     }
 
     // ------------------------------------------------------------------------------- transmitter / channel / monitor

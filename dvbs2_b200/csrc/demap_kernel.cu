@@ -102,7 +102,8 @@ demap_frames_kernel(const DemapLaunch a, float* __restrict__ llr, int deinterlea
     if (k >= a.n_sym) return;
     const float sg = a.sigma[f];
     const float inv = 1.0f / (2 * sg * sg);
-    const float2 y = reinterpret_cast<const float2*>(a.sym + (size_t)f * 2 * a.n_sym)[k];
+    const float2 y = a.pl_sym > 0 ? reinterpret_cast<const float2*>(a.sym + (size_t)f * 2 * a.pl_sym)[pl_symbol_pos(k, a.n_sym)]
+                                  : reinterpret_cast<const float2*>(a.sym + (size_t)f * 2 * a.n_sym)[k];
     float out[BPS];
     demap_symbol<BPS>(y.x, y.y, inv, cs, out);
     float* o = llr + (size_t)f * N_LDPC;
@@ -121,10 +122,14 @@ struct LaneVec<float, 2>
     __device__ static T make(const float* x) { return make_float2(x[0], x[1]); }
 };
 template<>
-struct LaneVec<int16_t, 2>
+struct LaneVec<int16_t, 4>
 {
-    using T = uint32_t;
-    __device__ static T make(const int16_t* x) { return (uint32_t)(uint16_t)x[0] | ((uint32_t)(uint16_t)x[1] << 16); }
+    using T = uint2;
+    __device__ static T make(const int16_t* x)
+    {
+        return make_uint2((uint32_t)(uint16_t)x[0] | ((uint32_t)(uint16_t)x[1] << 16),
+                          (uint32_t)(uint16_t)x[2] | ((uint32_t)(uint16_t)x[3] << 16));
+    }
 };
 template<>
 struct LaneVec<int8_t, 4>
@@ -157,15 +162,17 @@ __global__ void __launch_bounds__(DemapCfg<NF>::WARPS * 32) demap_to_var_kernel(
     const int g = blockIdx.y; // decoder group
     const int k0 = (blockIdx.x * WARPS + warp) * 16;
     if (k0 >= a.n_sym) return;
-    const int nfl = 2 * a.n_sym;
-    const int e = 2 * k0 + lane;
+    // row length and position of symbol k0 in it; a tile of 16 symbols never straddles a pilot block (1440 = 90 * 16)
+    const int nfl = a.pl_sym > 0 ? 2 * a.pl_sym : 2 * a.n_sym;
+    const int e = (a.pl_sym > 0 ? 2 * pl_symbol_pos(k0, a.n_sym) : 2 * k0) + lane;
+    const bool in_frame = 2 * k0 + lane < 2 * a.n_sym;
 #pragma unroll
     for (int j = 0; j < NF; j++)
 #pragma unroll 16
         for (int r = 0; r < 32; r++)
         {
             const int f = (g * NF + j) * 32 + r;
-            tile[warp][j][r][lane] = (f < a.n_frames && e < nfl) ? __ldg(a.sym + (size_t)f * nfl + e) : 0.f;
+            tile[warp][j][r][lane] = (f < a.n_frames && in_frame) ? __ldg(a.sym + (size_t)f * nfl + e) : 0.f;
         }
     __syncwarp();
     float inv[NF];
@@ -203,6 +210,71 @@ __global__ void __launch_bounds__(DemapCfg<NF>::WARPS * 32) demap_to_var_kernel(
             vg[(size_t)v * 32] = LaneVec<R, NF>::make(q[b]);
         }
     }
+}
+
+// Framer::remove_plh (src/common/Module/Framer/Framer.hxx:330-343) as a plain copy
+__global__ void
+remove_plh_kernel(const float2* __restrict__ pl, float2* __restrict__ out, int n_sym, int pl_sym)
+{
+    const int f = blockIdx.x;
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    if (k >= n_sym) return;
+    out[(size_t)f * n_sym + k] = pl[(size_t)f * pl_sym + pl_symbol_pos(k, n_sym)];
+}
+
+// Estimator_DVBS2::_estimate (src/common/Module/Estimator/Estimator_DVBS2.hxx:31-58): M2/M4 moments of the frame's payload
+// symbols, summed in float in symbol order exactly like the reference loop (no FMA contraction), then
+// Se = sqrt|2 M2^2 - M4|, Ne = |M2 - Se|, Es/N0 = 10 log10(Se / Ne) (100 dB if infinite), sigma = esn0_to_sigma(Es/N0),
+// Eb/N0 = esn0_to_ebn0(Es/N0, K_bch / 16200, bps) (lib/aff3ct/src/Tools/general_utils.cpp:78-113).
+// warp = 32 frames (lane = frame, so every frame's sum runs in the reference's order); the symbols pass through shared
+// memory in tiles of 16 so that global reads are 128-byte rows of one frame.  Two tiles are in flight per warp.
+__global__ void __launch_bounds__(128) estimate_kernel(const DemapLaunch a, int K_bch, float* __restrict__ sigma,
+                                                       float* __restrict__ ebn0, float* __restrict__ esn0)
+{
+    __shared__ float tile[4][2][32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sg = blockIdx.x * 4 + warp;
+    if (sg * 32 >= a.n_frames) return;
+    const int nfl = a.pl_sym > 0 ? 2 * a.pl_sym : 2 * a.n_sym;
+    const int n_tiles = (a.n_sym + 15) / 16;
+    auto stage = [&](int tl, int buf) {
+        const int k0 = tl * 16;
+        const int e = (a.pl_sym > 0 ? 2 * pl_symbol_pos(k0, a.n_sym) : 2 * k0) + lane;
+        const bool in_frame = 2 * k0 + lane < 2 * a.n_sym;
+#pragma unroll 16
+        for (int r = 0; r < 32; r++)
+        {
+            const int f = sg * 32 + r;
+            tile[warp][buf][r][lane] = (f < a.n_frames && in_frame) ? __ldg(a.sym + (size_t)f * nfl + e) : 0.f;
+        }
+    };
+    float m2 = 0.f, m4 = 0.f;
+    stage(0, 0);
+    for (int tl = 0; tl < n_tiles; tl++)
+    {
+        __syncwarp();
+        if (tl + 1 < n_tiles) stage(tl + 1, (tl + 1) & 1);
+        const int ns = min(16, a.n_sym - tl * 16);
+        for (int s = 0; s < ns; s++)
+        {
+            const float re = tile[warp][tl & 1][lane][2 * s], im = tile[warp][tl & 1][lane][2 * s + 1];
+            const float tmp = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+            m2 = __fadd_rn(m2, tmp);
+            m4 = __fadd_rn(m4, __fmul_rn(tmp, tmp));
+        }
+        __syncwarp();
+    }
+    const int f = sg * 32 + lane;
+    if (f >= a.n_frames) return;
+    m2 = __fdiv_rn(m2, (float)a.n_sym);
+    m4 = __fdiv_rn(m4, (float)a.n_sym);
+    const float Se = sqrtf(fabsf(__fsub_rn(__fmul_rn(__fmul_rn(2.f, m2), m2), m4)));
+    const float Ne = fabsf(__fsub_rn(m2, Se));
+    float e = 10.f * log10f(__fdiv_rn(Se, Ne));
+    if (isinf(e)) e = 100.f;
+    sigma[f] = sqrtf(__fdiv_rn(1.f, 2.f * powf(10.f, __fdiv_rn(e, 10.f))));
+    if (ebn0) ebn0[f] = e - 10.f * log10f(((float)K_bch / 16200.f) * (float)a.bps);
+    if (esn0) esn0[f] = e;
 }
 
 __global__ void
@@ -252,12 +324,12 @@ template<int BPS>
 static cudaError_t
 demap_to_var_bps(const DemapLaunch& a, void* var, int precision, int nf, cudaStream_t s)
 {
-    // the group width is fixed by the precision (ldpc_frames_per_lane): 2 for float and int16, 4 for int8
-    if (nf != (precision == 2 ? 4 : 2)) return cudaErrorInvalidValue;
+    // the group width is fixed by the precision (ldpc_frames_per_lane): 2 for float, 4 for int16 and int8
+    if (nf != (precision == 0 ? 2 : 4)) return cudaErrorInvalidValue;
     switch (precision)
     {
         case 0: demap_to_var_launch<BPS, float, 2>(a, var, s); break;
-        case 1: demap_to_var_launch<BPS, int16_t, 2>(a, var, s); break;
+        case 1: demap_to_var_launch<BPS, int16_t, 4>(a, var, s); break;
         case 2: demap_to_var_launch<BPS, int8_t, 4>(a, var, s); break;
         default: return cudaErrorInvalidValue;
     }
@@ -274,6 +346,22 @@ launch_demap_to_var(const DemapLaunch& a, void* var, int precision, int nf, cuda
         case 4: return demap_to_var_bps<4>(a, var, precision, nf, s);
     }
     return cudaErrorInvalidValue;
+}
+
+cudaError_t
+launch_remove_plh(const float* pl, float* out, int n_sym, int n_frames, cudaStream_t s)
+{
+    const dim3 grid(n_frames, (n_sym + 255) / 256);
+    remove_plh_kernel<<<grid, 256, 0, s>>>((const float2*)pl, (float2*)out, n_sym, pl_frame_symbols(n_sym));
+    return cudaGetLastError();
+}
+
+cudaError_t
+launch_estimate(const DemapLaunch& a, int K_bch, float* sigma, float* ebn0, float* esn0, cudaStream_t s)
+{
+    const int subgroups = (a.n_frames + 31) / 32;
+    estimate_kernel<<<(subgroups + 3) / 4, 128, 0, s>>>(a, K_bch, sigma, ebn0, esn0);
+    return cudaGetLastError();
 }
 
 cudaError_t

@@ -94,7 +94,9 @@ int ldpc_later_frames_per_lane(int precision, int preferred);
 int ldpc_frames_per_lane(int precision); // NF: 2 (f32, i16), 4 (i8)
 cudaError_t launch_ldpc_decode(const LdpcLaunch& a, int precision, cudaStream_t s);
 cudaError_t launch_pack_llr(const void* in, void* var, int precision, int n_frames, cudaStream_t s);
-cudaError_t launch_unpack_bits(const uint32_t* words, int32_t* out, int stride, int K, int n_frames, cudaStream_t s);
+// scr (optional): BB scrambler sequence, 8 bits per byte LSB first, XORed into the output (Scrambler_BB::descramble)
+cudaError_t launch_unpack_bits(const uint32_t* words, int32_t* out, int stride, int K, int n_frames, cudaStream_t s,
+                               const uint8_t* scr = nullptr);
 cudaError_t launch_unpack_bytes(const uint32_t* words, const uint8_t* scr, uint8_t* out, int stride, int K, int n_frames,
                                 cudaStream_t s);
 cudaError_t launch_pack_bits(const int32_t* in, uint32_t* words, int stride, int N, int n_frames, cudaStream_t s);
@@ -108,7 +110,26 @@ struct DemapLaunch
     int bps, n_sym;
     int itl_cols, itl_rev;
     int quant_dec, quant_bits; // for integer outputs
+    int pl_sym;                // > 0: sym holds whole PL frames [frames][2*pl_sym]; the payload symbols are picked out in place
+                               // (Framer::remove_plh fused into the read side), 0: sym holds XFEC frames
 };
+// PL frame geometry (src/common/Module/Framer/Framer.hxx:36-38,330-343; src/common/Factory/DVBS2/DVBS2.cpp:352-355): 90-symbol
+// header, then the payload with a 36-symbol pilot block after every 1440 payload symbols (n_sym / 1440 blocks in all)
+__host__ __device__ inline int
+pl_frame_symbols(int n_sym)
+{
+    return 90 * (n_sym / 90 + 1) + 36 * (n_sym / 1440);
+}
+__host__ __device__ inline int
+pl_symbol_pos(int k, int n_sym) // PL-frame position of payload symbol k
+{
+    const int blocks = k / 1440, n_pilots = n_sym / 1440;
+    return 90 + k + 36 * (blocks < n_pilots ? blocks : n_pilots);
+}
+// Framer::remove_plh as a copy: [frames][2*pl_sym] -> [frames][2*n_sym]
+cudaError_t launch_remove_plh(const float* pl, float* out, int n_sym, int n_frames, cudaStream_t s);
+// Estimator_DVBS2::estimate: per frame sigma (and optionally Eb/N0, Es/N0 in dB) from the M2/M4 moments of its payload symbols
+cudaError_t launch_estimate(const DemapLaunch& a, int K_bch, float* sigma, float* ebn0, float* esn0, cudaStream_t s);
 // frame-major float LLRs; deinterleave = 0 gives Modem::demodulate order, 1 gives natural order
 cudaError_t launch_demap_frames(const DemapLaunch& a, float* llr, int deinterleave, cudaStream_t s);
 // straight into the decoder's lane-interleaved var layout (natural order, nf frames per lane), quantised for integers

@@ -143,6 +143,37 @@ struct RawVec<16>
     using T = uint4;
 };
 
+
+// ---------------------------------------------------------------------------------------------- packed int16 pairs
+// Two frames per 32-bit word (low / high half), sm_100a packed-halfword instructions (VIADD.16x2, VIMNMX.S16x2).  Every
+// operation is the ring operation modulo 2^16 per half, i.e. exactly the reference's int16_t arithmetic with its wraps.
+namespace pk
+{
+__device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+__device__ __forceinline__ uint32_t neg(uint32_t a) { return __vadd2(~a, 0x00010001u); }
+__device__ __forceinline__ uint32_t vmin(uint32_t a, uint32_t b) { return __vmins2(a, b); }
+__device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+// |t| with the reference's wrap (|-32768| = -32768): max(t, -t) as signed halves
+__device__ __forceinline__ uint32_t absv(uint32_t t) { return __vmaxs2(t, neg(t)); }
+// 0xffff in every half whose bit 15 is set
+// (prmt's sign-replicate selector, bit 3 of a nibble; __byte_perm() masks that bit off, hence the PTX)
+__device__ __forceinline__ uint32_t signmask(uint32_t x)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xbb99;" : "=r"(r) : "r"(x));
+    return r;
+}
+// 0xffff in the low / high half if bit b / bit 16 + b of w is set (b = 0..15, compile-time)
+__device__ __forceinline__ uint32_t bitmask(uint32_t w, int b) { return signmask(w << (15 - b)); }
+// per half: m ? a : b
+__device__ __forceinline__ uint32_t mux(uint32_t a, uint32_t b, uint32_t m) { return (a & m) | (b & ~m); }
+// 0xffff in every half of x that is zero
+__device__ __forceinline__ uint32_t zeromask(uint32_t x) { return signmask(__vadd2(x, 0xffffffffu) & ~x & 0x80008000u); }
+__device__ __forceinline__ int lo(uint32_t x) { return (int)(short)(x & 0xffffu); }
+__device__ __forceinline__ int hi(uint32_t x) { return (int)(short)(x >> 16); }
+__device__ __forceinline__ uint32_t pair(int l, int h) { return ((uint32_t)l & 0xffffu) | ((uint32_t)h << 16); }
+} // namespace pk
+
 // ---------------------------------------------------------------------------------------------- the decoder
 template<typename R, int DI, int NF>
 struct CheckRegs
@@ -151,9 +182,16 @@ struct CheckRegs
     uint4 st[NF];                                 // compressed check state of the previous iteration
 };
 
-template<typename R, int DI, int NF>
+// PK (int16_t, NF = 4 only): the check loop works on packed pairs of frames — lane l holds frames (l, 32 + l) in word 0
+// and (64 + l, 96 + l) in word 1 of its 8-byte vector, so a variable is again one 256-byte chunk per warp but for 128 frames,
+// and every arithmetic instruction serves two frames.  Check state per pair and check (one uint4): the two output
+// magnitudes as pairs, the sign bits of edges 0..15 (bit e: first frame, bit 16 + e: second frame), the sign bits of edges
+// 16.. in the same arrangement with the index of one edge attaining min1 in bits 11..15 / 27..31 (with ties min2 = min1,
+// so any such edge reproduces the reference's value-equality rule).
+template<typename R, int DI, int NF, bool PK = false>
 __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const LdpcLaunch a)
 {
+    static_assert(!PK || (sizeof(R) == 2 && NF == 4), "packed pairs: int16_t, four frames per lane");
     using A = Arith<R>;
     using C = typename A::C;
     using Raw = typename RawVec<sizeof(R) * NF>::T;
@@ -220,6 +258,153 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
             for (int j = 0; j < NF; j++)
                 mine_any |= mine[j];
 
+            if constexpr (PK)
+            {
+                constexpr int NP = 2;         // pairs per lane
+                constexpr uint32_t ONE = 0x00010001u, MAXV = 0x7fff7fffu;
+                uint4* __restrict__ cnp = a.cn + (size_t)g * M * NP * 32 + lane; // [c][pair][lane]
+                const bool have_state = resumed || ite > 0;
+                bool pmine[NP];
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+                    pmine[p] = mine[2 * p] || mine[2 * p + 1];
+                uint32_t chain[NP];
+#pragma unroll
+                for (int p = 0; p < NP; p++)
+                    chain[p] = MAXV;
+                // x[i]: what the warp holds for edge i of the current check — first the loaded variable (both pairs), then, in
+                // place, t = var - msg.  Pass 2 consumes x[i] and immediately requests edge i of the NEXT check into the same
+                // registers (hazard-free: checks c and c+1 share no information variable, see header), so the loads of check
+                // c+1 trickle out during pass 2 of check c and only ~D vector registers are live instead of 2 D.
+                uint2 x[D];
+                uint4 rst[NP];
+                auto load_var = [&](int c, int i) { // i < DI: i-th information variable of check c;  i == DI + 1: var[K + c]
+                    unsigned vi = (unsigned)(K + c);
+                    if (i < DI) vi = (s_idx[c * IW + (i >> 1)] >> ((i & 1) * 16)) & 0xffffu;
+                    x[i] = __ldcg(reinterpret_cast<const uint2*>(vbytes + (vi * VB + loff)));
+                };
+                auto load_state = [&](int c) {
+#pragma unroll
+                    for (int p = 0; p < NP; p++)
+                        rst[p] = have_state ? __ldcg(cnp + (size_t)(c * NP + p) * 32) : make_uint4(0u, 0u, 0u, 0u);
+                };
+#pragma unroll
+                for (int i = 0; i < D; i++)
+                    if (i != DI) load_var(0, i);
+                load_state(0);
+#pragma unroll 1
+                for (int c = 0; c < M; c++)
+                {
+                    const uint32_t* row = s_idx + c * IW;
+                    const uint32_t lastm = s_last[c];
+                    const bool more = c + 1 < M;
+                    uint32_t min1[NP], c1[NP], c2[NP], sacc[NP];
+#pragma unroll
+                    for (int p = 0; p < NP; p++)
+                    {
+                        const uint32_t o1 = rst[p].x, o2 = rst[p].y, S0 = rst[p].z, S1 = rst[p].w;
+                        const uint32_t no1 = pk::neg(o1), no2 = pk::neg(o2);
+                        const uint32_t ohA = 1u << ((S1 >> 11) & 31u), ohB = 1u << (S1 >> 27);
+                        const uint32_t E0 = __byte_perm(ohA, ohB, 0x5410), E1 = __byte_perm(ohA, ohB, 0x7632);
+                        uint32_t sa = 0, m1 = MAXV, m2 = MAXV;
+#pragma unroll
+                        for (int i = 0; i < D; i++)
+                        {
+                            const uint32_t v = (i == DI) ? chain[p] : (p == 0 ? x[i].x : x[i].y);
+                            const int b = i & 15;
+                            const uint32_t sm = pk::bitmask(i < 16 ? S0 : S1, b), em = pk::bitmask(i < 16 ? E0 : E1, b);
+                            // t = v - msg (Update_rule_MS.hxx:57-67): add -mag for a positive message, +mag for a negative one
+                            uint32_t ti = pk::add(v, pk::mux(pk::mux(o1, o2, em), pk::mux(no1, no2, em), sm));
+                            if (i == DI && c == 0) ti = MAXV; // check 0 has no incoming chain edge
+                            if (p == 0)
+                                x[i].x = ti;
+                            else
+                                x[i].y = ti;
+                            const uint32_t ab = pk::absv(ti);
+                            sa ^= ti;
+                            m2 = pk::vmin(m2, pk::vmax(ab, m1));
+                            m1 = pk::vmin(m1, ab);
+                        }
+                        min1[p] = m1, sacc[p] = sa;
+                        uint32_t n2 = m2, n1 = m1;
+                        if (a.k8 != 8)
+                        { // Update_rule_NMS.hxx:14-39, per half
+                            n2 = pk::pair(Arith<int16_t>::normalize(pk::lo(m2), a.norm, a.k8), Arith<int16_t>::normalize(pk::hi(m2), a.norm, a.k8));
+                            n1 = pk::pair(Arith<int16_t>::normalize(pk::lo(m1), a.norm, a.k8), Arith<int16_t>::normalize(pk::hi(m1), a.norm, a.k8));
+                        }
+                        c1[p] = pk::vmax(0u, n2), c2[p] = pk::vmax(0u, n1); // Update_rule_NMS.hxx:100-106
+                    }
+                    if (more) load_state(c + 1);
+
+                    uint32_t ns0[NP], ns1[NP], nidx[NP];
+#pragma unroll
+                    for (int p = 0; p < NP; p++)
+                        ns0[p] = ns1[p] = nidx[p] = 0;
+#pragma unroll
+                    for (int i = 0; i < D; i++)
+                    {
+                        uint32_t nv[NP];
+                        const int b = i & 15;
+#pragma unroll
+                        for (int p = 0; p < NP; p++)
+                        {
+                            uint32_t ti = p == 0 ? x[i].x : x[i].y;
+                            asm volatile("" : "+r"(ti)); // |t| is recomputed here, not kept in registers since pass 1
+                            const uint32_t em = pk::zeromask(pk::absv(ti) ^ min1[p]); // |t| == min1
+                            const uint32_t xs = sacc[p] ^ ti;                         // bits 15 / 31: sign of the new message
+                            const uint32_t sm = pk::signmask(xs), s1 = (xs >> 15) & ONE;
+                            // t + sign * mag with -mag = (mag ^ 0xffff) + 1 per half
+                            nv[p] = pk::add(pk::add(ti, pk::mux(c1[p], c2[p], em) ^ sm), s1);
+                            nidx[p] = pk::mux((uint32_t)i * ONE, nidx[p], em);
+                            const uint32_t sb = s1 << b;
+                            if (i < 16)
+                                ns0[p] |= sb;
+                            else
+                                ns1[p] |= sb;
+                        }
+                        if (i != DI && more) load_var(c + 1, i); // x[i] is free from here on
+                        unsigned vi;
+                        bool ballot;
+                        if (i < DI)
+                        {
+                            vi = (row[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+                            ballot = (lastm >> i) & 1u;
+                        }
+                        else if (i == DI)
+                        {
+                            if (c == 0) continue;
+                            vi = K + c - 1;
+                            ballot = true;
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int p = 0; p < NP; p++)
+                                chain[p] = nv[p];
+                            if (c != M - 1) continue;
+                            vi = K + c;
+                            ballot = true;
+                        }
+                        if (mine_any) __stcg(reinterpret_cast<uint2*>(vbytes + (vi * VB + loff)), make_uint2(nv[0], nv[1]));
+                        if (ballot) // warp-uniform: only the last update of a variable in the iteration fixes its hard decision
+                        {
+                            uint4 hw;
+                            hw.x = __ballot_sync(FULL, (nv[0] & 0x8000u) != 0);
+                            hw.y = __ballot_sync(FULL, (int)nv[0] < 0);
+                            hw.z = __ballot_sync(FULL, (nv[1] & 0x8000u) != 0);
+                            hw.w = __ballot_sync(FULL, (int)nv[1] < 0);
+                            if (lane == 0) __stcg(reinterpret_cast<uint4*>(hd + (size_t)vi * NF), hw);
+                        }
+                    }
+#pragma unroll
+                    for (int p = 0; p < NP; p++)
+                        if (pmine[p])
+                            __stcg(cnp + (size_t)(c * NP + p) * 32,
+                                   make_uint4(c1[p], c2[p], ns0[p], ns1[p] | ((nidx[p] & 0x001f001fu) << 11)));
+                }
+            }
+            else
+            {
             C chain[NF]; // var[K+c-1] after check c-1; for c = 0 a neutral dummy edge
 #pragma unroll
             for (int j = 0; j < NF; j++)
@@ -360,6 +545,7 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
                         const unsigned lo = A::pack(c1[j], c2[j], hi);
                         __stcg(cn + (size_t)(c * NF + j) * 32, make_uint4(lo, hi, nsg[j], neq[j]));
                     }
+            }
             }
 #pragma unroll
             for (int j = 0; j < NF; j++)
@@ -582,13 +768,50 @@ __global__ void __launch_bounds__(128) compact_copy_kernel(const CompactLaunch c
         for (int j = 0; j < ND; j++)
             vd[(size_t)v * 32 * ND + j] = x[j];
     }
-    uint4* cd = c.cn_dst + (size_t)d * c.M * ND * 32 + lane;
+    uint4* cd = c.cn_dst + (size_t)d * c.M * (sizeof(R) == 2 ? ND / 2 : ND) * 32 + lane;
     const int c0 = (int)((long)c.M * part / COMPACT_PARTS), c1 = (int)((long)c.M * (part + 1) / COMPACT_PARTS);
-#pragma unroll 2
-    for (int k = c0; k < c1; k++)
+    if constexpr (sizeof(R) == 2)
+    { // packed pairs (ldpc_decode_kernel<int16_t, ., 4, true>): state [check][pair][lane], one half of every word per frame
+        static_assert(NF == 4 && ND == 4, "int16_t groups hold four frames per lane");
+        size_t pbase[ND];
+        int sh[ND];
 #pragma unroll
         for (int j = 0; j < ND; j++)
-            cd[(size_t)(k * ND + j) * 32] = valid[j] ? __ldcg(c.cn_src + cbase[j] + (size_t)k * NF * 32) : make_uint4(0u, 0u, 0u, 0u);
+        {
+            const int ds = (d * ND + j) * 32 + lane;
+            const int s = valid[j] ? c.src_of_dst[ds] : 0;
+            const int gs = s / (32 * NF), js = (s / 32) % NF, ls = s % 32;
+            pbase[j] = ((size_t)gs * c.M * (NF / 2) + (js >> 1)) * 32 + ls;
+            sh[j] = (js & 1) * 16;
+        }
+#pragma unroll 2
+        for (int k = c0; k < c1; k++)
+#pragma unroll
+            for (int p = 0; p < ND / 2; p++)
+            {
+                uint32_t w[4] = { 0u, 0u, 0u, 0u };
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++)
+                {
+                    const int j = 2 * p + hf;
+                    if (!valid[j]) continue;
+                    const uint4 x = __ldcg(c.cn_src + pbase[j] + (size_t)k * 2 * 32);
+                    w[0] |= ((x.x >> sh[j]) & 0xffffu) << (16 * hf);
+                    w[1] |= ((x.y >> sh[j]) & 0xffffu) << (16 * hf);
+                    w[2] |= ((x.z >> sh[j]) & 0xffffu) << (16 * hf);
+                    w[3] |= ((x.w >> sh[j]) & 0xffffu) << (16 * hf);
+                }
+                cd[(size_t)(k * 2 + p) * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+    }
+    else
+    {
+#pragma unroll 2
+        for (int k = c0; k < c1; k++)
+#pragma unroll
+            for (int j = 0; j < ND; j++)
+                cd[(size_t)(k * ND + j) * 32] = valid[j] ? __ldcg(c.cn_src + cbase[j] + (size_t)k * NF * 32) : make_uint4(0u, 0u, 0u, 0u);
+    }
 }
 
 // after the last round: the final hard decisions of every frame handed over by round 1 go back to the bit lane of its
@@ -654,12 +877,14 @@ pack_llr_kernel(const R* __restrict__ in, R* __restrict__ var, int n_frames, int
 
 // bit-sliced words [subgroup][stride] -> int32 bits [F][K] (first K variables)
 __global__ void
-unpack_bits_kernel(const uint32_t* __restrict__ words, int32_t* __restrict__ out, int stride, int K, int n_frames)
+unpack_bits_kernel(const uint32_t* __restrict__ words, const uint8_t* __restrict__ scr, int32_t* __restrict__ out, int stride,
+                   int K, int n_frames)
 {
     const int g = blockIdx.y;
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= K) return;
-    const uint32_t w = words[(size_t)g * stride + v];
+    uint32_t w = words[(size_t)g * stride + v];
+    if (scr && ((scr[v >> 3] >> (v & 7)) & 1u)) w = ~w; // Scrambler_BB::descramble: XOR with the PRBS bit of position v
 #pragma unroll 8
     for (int f = 0; f < 32; f++)
     {
@@ -720,14 +945,14 @@ pack_bits_kernel(const int32_t* __restrict__ in, uint32_t* __restrict__ words, i
 int
 ldpc_frames_per_lane(int precision)
 {
-    return precision == 0 ? 2 : precision == 1 ? 2 : 4;
+    return precision == 0 ? 2 : 4; // float: 2 x 4 B, int16: 4 x 2 B (packed pairs), int8: 4 x 1 B per lane and variable
 }
 
-template<typename R, int DI, int NF>
+template<typename R, int DI, int NF, bool PK = false>
 static cudaError_t
 launch_ldpc_k(const LdpcLaunch& a, cudaStream_t s)
 {
-    auto k = ldpc_decode_kernel<R, DI, NF>;
+    auto k = ldpc_decode_kernel<R, DI, NF, PK>;
     const size_t smem = ((size_t)a.M * ((DI + 1) / 2) + a.M) * sizeof(uint32_t);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); // per device
     if (e != cudaSuccess) return e;
@@ -741,12 +966,12 @@ launch_ldpc_k(const LdpcLaunch& a, cudaStream_t s)
     return cudaGetLastError();
 }
 
-template<typename R, int NF>
+template<typename R, int NF, bool PK = false>
 static cudaError_t
 launch_ldpc_t(const LdpcLaunch& a, cudaStream_t s)
 {
-    if (a.d_info == 25) return launch_ldpc_k<R, 25, NF>(a, s);
-    if (a.d_info == 9) return launch_ldpc_k<R, 9, NF>(a, s);
+    if (a.d_info == 25) return launch_ldpc_k<R, 25, NF, PK>(a, s);
+    if (a.d_info == 9) return launch_ldpc_k<R, 9, NF, PK>(a, s);
     return cudaErrorInvalidValue;
 }
 
@@ -756,7 +981,7 @@ launch_ldpc_decode(const LdpcLaunch& a, int precision, cudaStream_t s)
     switch (precision)
     {
         case 0: return a.nf == 1 ? launch_ldpc_t<float, 1>(a, s) : launch_ldpc_t<float, 2>(a, s);
-        case 1: return launch_ldpc_t<int16_t, 2>(a, s);
+        case 1: return launch_ldpc_t<int16_t, 4, true>(a, s);
         case 2: return launch_ldpc_t<int8_t, 4>(a, s);
     }
     return cudaErrorInvalidValue;
@@ -794,7 +1019,7 @@ launch_compact(const CompactLaunch& c, int precision, cudaStream_t s)
             if (c.nf == 1 && c.nf_dst == 1) return launch_compact_t<float, 1, 1>(c, s);
             break;
         case 1:
-            if (c.nf == 2 && c.nf_dst == 2) return launch_compact_t<int16_t, 2, 2>(c, s);
+            if (c.nf == 4 && c.nf_dst == 4) return launch_compact_t<int16_t, 4, 4>(c, s);
             break;
         case 2:
             if (c.nf == 4 && c.nf_dst == 4) return launch_compact_t<int8_t, 4, 4>(c, s);
@@ -828,11 +1053,11 @@ launch_pack_llr(const void* in, void* var, int precision, int n_frames, cudaStre
 }
 
 cudaError_t
-launch_unpack_bits(const uint32_t* words, int32_t* out, int stride, int K, int n_frames, cudaStream_t s)
+launch_unpack_bits(const uint32_t* words, int32_t* out, int stride, int K, int n_frames, cudaStream_t s, const uint8_t* scr)
 {
     const int groups = (n_frames + 31) / 32;
     const dim3 grid((K + 127) / 128, groups);
-    unpack_bits_kernel<<<grid, 128, 0, s>>>(words, out, stride, K, n_frames);
+    unpack_bits_kernel<<<grid, 128, 0, s>>>(words, scr, out, stride, K, n_frames);
     return cudaGetLastError();
 }
 

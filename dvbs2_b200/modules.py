@@ -257,6 +257,65 @@ class Decoder_chain_DVBS2_cuda(_Module):
             None if n_iter is None else _dev_ptr(n_iter, "int32", F, "n_iter"), int(bool(descramble)), F))
 
 
+class Framer_DVBS2_cuda(_Module):
+    """Framer<float>::remove_plh on the device (src/common/Module/Framer/Framer.hxx:319-343)."""
+
+    def __init__(self, handle, n_frames=1):
+        super().__init__(handle, n_frames)
+        self.xfec_frame_size = 2 * handle.info["n_sym"]
+        self.pl_frame_size = handle.lib.dvbs2_cuda_pl_frame_size(handle._h)
+
+    def remove_plh(self, Y_N1, Y_N2):
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_remove_plh(h._h, _np_ptr(Y_N1, np.float32, F * self.pl_frame_size, "Y_N1"),
+                                            _np_ptr(Y_N2, np.float32, F * self.xfec_frame_size, "Y_N2"), F))
+
+
+class Estimator_DVBS2_cuda(_Module):
+    """Estimator_DVBS2<float>::estimate on the device (src/common/Module/Estimator/Estimator_DVBS2.hxx:31-58)."""
+
+    def __init__(self, handle, n_frames=1):
+        super().__init__(handle, n_frames)
+        self.N = 2 * handle.info["n_sym"]
+
+    def estimate(self, X_N, SIG, Eb_N0=None, Es_N0=None):
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_estimate(
+            h._h, _np_ptr(X_N, np.float32, F * self.N, "X_N"), _np_ptr(SIG, np.float32, F, "SIG"),
+            None if Eb_N0 is None else _np_ptr(Eb_N0, np.float32, F, "Eb_N0"),
+            None if Es_N0 is None else _np_ptr(Es_N0, np.float32, F, "Es_N0"), F))
+
+
+class Receiver_chain_DVBS2_cuda(_Module):
+    """Fused receiver stage from PL frames: remove_plh -> estimate (or caller's sigma) -> demodulate -> deinterleave -> LDPC ->
+    BCH -> optional BB descramble; int32 or bit-packed output (SURVEY §8f N1 + N2)."""
+
+    def __init__(self, handle, n_frames=1):
+        super().__init__(handle, n_frames)
+        self.K = handle.info["K_bch"]
+        self.pl_frame_size = handle.lib.dvbs2_cuda_pl_frame_size(handle._h)
+
+    def receive(self, PL_frames, CP=None, SIG=None, CWD_ldpc=None, CWD_bch=None, V_K=None, V_K_packed=None, n_iter=None,
+                descramble=True):
+        F, h = self.n_frames, self.h
+        opt = lambda a, dt, n, name: None if a is None else _np_ptr(a, dt, n, name)  # noqa: E731
+        h.check(h.lib.dvbs2_cuda_rx_chain(
+            h._h, _np_ptr(PL_frames, np.float32, F * self.pl_frame_size, "PL_frames"), opt(CP, np.float32, F, "CP"),
+            opt(SIG, np.float32, F, "SIG"), opt(CWD_ldpc, np.int8, F, "CWD_ldpc"), opt(CWD_bch, np.int8, F, "CWD_bch"),
+            opt(V_K, np.int32, F * self.K, "V_K"), opt(V_K_packed, np.uint8, F * (self.K // 8), "V_K_packed"),
+            int(bool(descramble)), opt(n_iter, np.int32, F, "n_iter"), F))
+
+    def receive_dev(self, PL_frames, CP=None, SIG=None, CWD_ldpc=None, CWD_bch=None, V_K=None, V_K_packed=None, n_iter=None,
+                    descramble=True):
+        F, h = self.n_frames, self.h
+        opt = lambda a, dt, n, name: None if a is None else _dev_ptr(a, dt, n, name)  # noqa: E731
+        h.check(h.lib.dvbs2_cuda_rx_chain_dev(
+            h._h, _dev_ptr(PL_frames, "float32", F * self.pl_frame_size, "PL_frames"), opt(CP, "float32", F, "CP"),
+            opt(SIG, "float32", F, "SIG"), opt(CWD_ldpc, "int8", F, "CWD_ldpc"), opt(CWD_bch, "int8", F, "CWD_bch"),
+            opt(V_K, "int32", F * self.K, "V_K"), opt(V_K_packed, "uint8", F * (self.K // 8), "V_K_packed"),
+            int(bool(descramble)), opt(n_iter, "int32", F, "n_iter"), F))
+
+
 class Transmitter_DVBS2_cuda(_Module):
     """On-device TX chain + AWGN channel + BFER monitor around the decode path (Monte-Carlo / benchmark harness):
     Source -> Scrambler_BB.scramble -> Encoder_BCH_DVBS2 -> Encoder_LDPC_DVBS2 -> interleave -> modulate -> add_noise

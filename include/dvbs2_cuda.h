@@ -155,6 +155,24 @@ extern "C"
     int dvbs2_cuda_chain_packed(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
                                 uint8_t* V_K_packed, int32_t* n_iter, int descramble, int n_frames);
 
+    /* ---- receiver stage from PL frames: the tasks bound in front of and behind the decode chain in
+     * src/mains/TX_RX_BB/main.cpp:86-92 and src/mains/RX/main_sched.cpp:204-211 ------------------------------------------- */
+
+    /* floats per PL frame = 2 * (90 * (n_sym / 90 + 1) + 36 * (n_sym / 1440)) (src/common/Factory/DVBS2/DVBS2.cpp:352-355) */
+    int dvbs2_cuda_pl_frame_size(const dvbs2_cuda_handle* h);
+    /* Framer::remove_plh (src/common/Module/Framer/Framer.hxx:319-343): Y_N1[F][pl_frame_size] -> Y_N2[F][2*n_sym]; drops the
+     * 90-symbol PL header and the 36-symbol pilot block after every 1440 payload symbols */
+    int dvbs2_cuda_remove_plh(dvbs2_cuda_handle* h, const float* Y_N1, float* Y_N2, int n_frames);
+    /* Estimator_DVBS2::estimate (src/common/Module/Estimator/Estimator.hxx:103-117, Estimator_DVBS2.hxx:31-58): X_N[F][2*n_sym]
+     * -> SIG[F], Eb_N0[F], Es_N0[F] (dB; the last two may be NULL).  M2/M4 moments summed in float in the reference's order. */
+    int dvbs2_cuda_estimate(dvbs2_cuda_handle* h, const float* X_N, float* SIG, float* Eb_N0, float* Es_N0, int n_frames);
+    /* Fused receiver stage: remove_plh -> estimate (when CP == NULL; SIG, optional, receives the estimates) or the caller's
+     * CP[F] -> demodulate -> deinterleave -> LDPC -> BCH -> (Scrambler_BB::descramble when descramble != 0).  Exactly one of
+     * V_K (int32 per bit, [F][K_bch]) and V_K_packed ([F][K_bch/8], Bit_packer layout) must be given.  The PL header and
+     * pilots are skipped on the read side of the demapper; only PL frames cross PCIe. */
+    int dvbs2_cuda_rx_chain(dvbs2_cuda_handle* h, const float* PL_frames, const float* CP, float* SIG, int8_t* CWD_ldpc,
+                            int8_t* CWD_bch, int32_t* V_K, uint8_t* V_K_packed, int descramble, int32_t* n_iter, int n_frames);
+
     /* pin / unpin a caller-owned host buffer (StreamPU socket buffers are stable after binding) */
     int dvbs2_cuda_host_register(dvbs2_cuda_handle* h, void* ptr, size_t bytes);
     int dvbs2_cuda_host_unregister(dvbs2_cuda_handle* h, void* ptr);
@@ -173,6 +191,14 @@ extern "C"
 
     int dvbs2_cuda_chain_packed_dev(dvbs2_cuda_handle* h, const float* d_CP, const float* d_Y_N1, int8_t* d_CWD_ldpc,
                                     int8_t* d_CWD_bch, uint8_t* d_V_K_packed, int32_t* d_n_iter, int descramble, int n_frames);
+
+    int dvbs2_cuda_remove_plh_dev(dvbs2_cuda_handle* h, const float* d_Y_N1, float* d_Y_N2, int n_frames);
+    int dvbs2_cuda_estimate_dev(dvbs2_cuda_handle* h, const float* d_X_N, float* d_SIG, float* d_Eb_N0, float* d_Es_N0,
+                                int n_frames);
+    /* d_CP == NULL: estimate on the device into d_SIG (required then) */
+    int dvbs2_cuda_rx_chain_dev(dvbs2_cuda_handle* h, const float* d_PL_frames, const float* d_CP, float* d_SIG,
+                                int8_t* d_CWD_ldpc, int8_t* d_CWD_bch, int32_t* d_V_K, uint8_t* d_V_K_packed, int descramble,
+                                int32_t* d_n_iter, int n_frames);
 
     /* ---- on-device transmitter, AWGN channel and BER/FER monitor ------------------------------------------------
      * Monte-Carlo / benchmark harness around the decode path: what D/mains/TX_RX_BB/main.cpp:75-84

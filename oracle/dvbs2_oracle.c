@@ -480,6 +480,67 @@ oracle_bb_scramble(int K, int n_frames, const int32_t* in, int32_t* out)
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------ framer / estimator */
+/* D/common/Module/Framer/Framer.hxx:330-343 (_remove_plh): drop the 90-symbol PL header, then the 36-symbol pilot block
+ * that follows every 16 slots (1440 symbols) of payload; N_pilots = n_sym / 1440 (Framer.hxx:36-38),
+ * pl_frame_size = 90 * (n_sym / 90 + 1) + 36 * N_pilots symbols (D/common/Factory/DVBS2/DVBS2.cpp:352-355).
+ * in: [F][2 * pl_sym] floats (I/Q interleaved), out: [F][2 * n_sym]. */
+int
+oracle_pl_frame_symbols(int n_sym)
+{
+    return 90 * (n_sym / 90 + 1) + 36 * (n_sym / 1440);
+}
+
+int
+oracle_remove_plh(int n_sym, int n_frames, const float* in, float* out)
+{
+    const int M = 90, P = 36, n_pilots = n_sym / (16 * M), pl = oracle_pl_frame_symbols(n_sym);
+    for (int f = 0; f < n_frames; f++)
+    {
+        const float* src = in + (size_t)f * 2 * pl;
+        float* dst = out + (size_t)f * 2 * n_sym;
+        int pos = M; /* symbol index in the PL frame */
+        for (int k = 0; k < n_sym; k++)
+        {
+            /* the i-th erase (i = 1..n_pilots) removes the P symbols that follow payload symbol 16*M*i - 1 */
+            if (k > 0 && k % (16 * M) == 0 && k / (16 * M) <= n_pilots) pos += P;
+            dst[2 * k] = src[2 * (pos + k)];
+            dst[2 * k + 1] = src[2 * (pos + k) + 1];
+        }
+    }
+    return 0;
+}
+
+/* D/common/Module/Estimator/Estimator_DVBS2.hxx:31-58 (_estimate, M2M4 moments, all float, summed in symbol order) with
+ * A/src/Tools/general_utils.cpp:78-89 (esn0_to_sigma) and :91-113 (esn0_to_ebn0); code_rate = K_bch / N_ldpc as floats
+ * (D/common/Factory/DVBS2/DVBS2.cpp:557).  X: [F][2 * n_sym]; outputs [F] each (Estimator.hxx:103-117). */
+int
+oracle_estimate(int n_sym, int K_bch, int bps, int n_frames, const float* X, float* sig, float* ebn0, float* esn0)
+{
+    const float code_rate = (float)K_bch / (float)16200;
+    for (int f = 0; f < n_frames; f++)
+    {
+        const float* x = X + (size_t)f * 2 * n_sym;
+        float m2 = 0, m4 = 0;
+        for (int i = 0; i < n_sym; i++)
+        {
+            const float tmp = x[2 * i] * x[2 * i] + x[2 * i + 1] * x[2 * i + 1];
+            m2 += tmp;
+            m4 += tmp * tmp;
+        }
+        m2 /= n_sym;
+        m4 /= n_sym;
+        const float Se = sqrtf(fabsf(2 * m2 * m2 - m4));
+        const float Ne = fabsf(m2 - Se);
+        float e = 10 * log10f(Se / Ne);
+        if (isinf(e)) e = 100.f;
+        sig[f] = sqrtf((float)1 / ((float)2 * powf((float)10, e / (float)10)));
+        if (ebn0) ebn0[f] = e - (float)10 * log10f(code_rate * (float)bps);
+        if (esn0) esn0[f] = e;
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------ interleaver */
 /* A/src/Tools/Interleaver/Column_row/Interleaver_core_column_row.cpp:59-87 (gen_lut TOP_LEFT / TOP_RIGHT) and
  * A/include/Tools/Interleaver/Interleaver_core.hxx:137-142 (pi_inv[pi[i]] = i); selection per MODCOD in

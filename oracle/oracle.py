@@ -130,6 +130,38 @@ class Oracle:
         self.lib.oracle_bb_scramble(K, U.shape[0], _p(U), _p(out))
         return out
 
+    def pl_frame_symbols(self, n_sym):
+        return int(self.lib.oracle_pl_frame_symbols(int(n_sym)))
+
+    def remove_plh(self, n_sym, Y):
+        """Framer::remove_plh: [F][2 * pl_sym] -> [F][2 * n_sym]."""
+        pl = self.pl_frame_symbols(n_sym)
+        Y = _c(Y, np.float32).reshape(-1, 2 * pl)
+        out = np.zeros((Y.shape[0], 2 * n_sym), np.float32)
+        self.lib.oracle_remove_plh(int(n_sym), Y.shape[0], _p(Y), _p(out))
+        return out
+
+    def insert_plh(self, n_sym, X, seed=0):
+        """Test helper (inverse of remove_plh): payload symbols into a PL frame whose header and pilot blocks hold
+        arbitrary values (the receiver path never reads them)."""
+        pl = self.pl_frame_symbols(n_sym)
+        X = _c(X, np.float32).reshape(-1, 2 * n_sym)
+        rng = np.random.default_rng(seed)
+        out = rng.standard_normal((X.shape[0], 2 * pl)).astype(np.float32)
+        k = np.arange(n_sym)
+        pos = 90 + k + 36 * np.minimum(k // 1440, n_sym // 1440)
+        out[:, 2 * pos] = X[:, 0::2]
+        out[:, 2 * pos + 1] = X[:, 1::2]
+        return out
+
+    def estimate(self, n_sym, K_bch, bps, X):
+        """Estimator_DVBS2::estimate: returns (sigma, Eb/N0 dB, Es/N0 dB), one value per frame."""
+        X = _c(X, np.float32).reshape(-1, 2 * n_sym)
+        F = X.shape[0]
+        sig, eb, es = (np.zeros(F, np.float32) for _ in range(3))
+        self.lib.oracle_estimate(int(n_sym), int(K_bch), int(bps), F, _p(X), _p(sig), _p(eb), _p(es))
+        return sig, eb, es
+
     def itl_lut(self, n_cols, order):
         pi = np.zeros(N_LDPC, np.uint32)
         inv = np.zeros(N_LDPC, np.uint32)
@@ -289,6 +321,25 @@ class Ref:
         self.lib.ref_demodulate(mc["bps"], self._mod[mc["cstl"]], _ORDER_NAME[mc["itl"]].encode(), F, _p(sigma), _p(sym),
                                 _p(itl), _p(nat), _p(cst))
         return itl, nat, cst.reshape(-1, 2)
+
+    def remove_plh(self, modcod, n_sym, pl_sym, Y):
+        Y = _c(Y, np.float32).reshape(-1, 2 * pl_sym)
+        out = np.zeros((Y.shape[0], 2 * n_sym), np.float32)
+        self.lib.ref_remove_plh(modcod.encode(), int(n_sym), int(pl_sym), Y.shape[0], _p(Y), _p(out))
+        return out
+
+    def framer_generate(self, modcod, n_sym, pl_sym, X):
+        X = _c(X, np.float32).reshape(-1, 2 * n_sym)
+        out = np.zeros((X.shape[0], 2 * pl_sym), np.float32)
+        self.lib.ref_framer_generate(modcod.encode(), int(n_sym), int(pl_sym), X.shape[0], _p(X), _p(out))
+        return out
+
+    def estimate(self, n_sym, K_bch, bps, X):
+        X = _c(X, np.float32).reshape(-1, 2 * n_sym)
+        F = X.shape[0]
+        sig, eb, es = (np.zeros(F, np.float32) for _ in range(3))
+        self.lib.ref_estimate(int(n_sym), int(K_bch), int(bps), F, _p(X), _p(sig), _p(eb), _p(es))
+        return sig, eb, es
 
     def descramble(self, K, x):
         x = _c(x, np.int32).reshape(-1, K)

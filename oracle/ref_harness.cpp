@@ -31,6 +31,8 @@
 #include "Module/Decoder_BCH_DVBS2/Decoder_BCH_DVBS2.hpp"
 #include "Module/Encoder_BCH_DVBS2/Encoder_BCH_DVBS2.hpp"
 #include "Module/Scrambler/Scrambler_BB/Scrambler_BB.hpp"
+#include "Module/Framer/Framer.hpp"
+#include "Module/Estimator/Estimator_DVBS2.hpp"
 
 using namespace aff3ct;
 
@@ -219,6 +221,30 @@ extern "C"
         module::Scrambler_BB<int> scr(K_bch, 1);
         for (int f = 0; f < n_frames; f++)
             scr.descramble(const_cast<int32_t*>(in) + (size_t)f * K_bch, out + (size_t)f * K_bch);
+        return 0;
+    }
+
+    // Framer::remove_plh (Framer.hxx:319-343) and Estimator_DVBS2::estimate (Estimator.hxx:103-117, Estimator_DVBS2.hxx:31-58)
+    int ref_remove_plh(const char* modcod, int n_sym, int pl_sym, int n_frames, const float* in, float* out)
+    {
+        module::Framer<float> fr(2 * n_sym, 2 * pl_sym, std::string(modcod), 1);
+        for (int f = 0; f < n_frames; f++)
+            fr.remove_plh(const_cast<float*>(in) + (size_t)f * 2 * pl_sym, out + (size_t)f * 2 * n_sym);
+        return 0;
+    }
+    int ref_framer_generate(const char* modcod, int n_sym, int pl_sym, int n_frames, const float* in, float* out)
+    {
+        module::Framer<float> fr(2 * n_sym, 2 * pl_sym, std::string(modcod), 1);
+        for (int f = 0; f < n_frames; f++)
+            fr.generate(const_cast<float*>(in) + (size_t)f * 2 * n_sym, out + (size_t)f * 2 * pl_sym);
+        return 0;
+    }
+    int ref_estimate(int n_sym, int K_bch, int bps, int n_frames, const float* X, float* sig, float* ebn0, float* esn0)
+    {
+        const float code_rate = (float)K_bch / (float)16200;
+        module::Estimator_DVBS2<float> est(2 * n_sym, code_rate, bps, 1);
+        for (int f = 0; f < n_frames; f++)
+            est.estimate(X + (size_t)f * 2 * n_sym, sig + f, ebn0 + f, esn0 + f);
         return 0;
     }
 

@@ -77,6 +77,25 @@ def test_normalisation_factors(oracle, norm, prec):
     assert np.array_equal(nit, no) and np.array_equal(cwd, co) and np.array_equal(V, Vo)
 
 
+@pytest.mark.parametrize("modcod", ["QPSK-S_8/9", "QPSK-S_3/5"])
+def test_int16_wraps_like_the_reference(oracle, modcod):
+    """int16 inputs far outside the quantiser's range make the reference's int16_t arithmetic overflow and wrap; the packed
+    halfword kernel must wrap identically (ring arithmetic modulo 2^16 per frame), norm 1 and k/8 factors alike."""
+    K = MODCODS[modcod]["N_bch"]
+    Y, _ = _llrs(oracle, modcod, 130, 4.0 if K == 14400 else 2.4, seed=9)
+    rng = np.random.default_rng(12)
+    q = np.clip(np.round(Y * 900.0), -32767, 32767).astype(np.int16)            # frames 0..: large, often saturated
+    q[40:80] = rng.integers(-32768, 32768, size=(40, N_LDPC)).astype(np.int16)    # pure noise over the full range
+    q[80:100] = np.clip(np.round(Y[80:100] * 4.0), -31, 31).astype(np.int16)      # the default 6-bit quantiser
+    q[100] = 0
+    q[101] = -32768
+    q[102] = 32767
+    for norm in (1.0, 0.75):
+        V, cwd, nit, _ = _decode(modcod, q, prec="i16", norm=norm)
+        Vo, co, no = oracle.ldpc_decode(K, q, prec="i16", norm=norm)
+        assert np.array_equal(nit, no) and np.array_equal(cwd, co) and np.array_equal(V, Vo)
+
+
 def test_no_early_stop_and_iteration_counts(oracle):
     Y, _ = _llrs(oracle, "QPSK-S_8/9", 64, 4.2)
     V, cwd, nit, _ = _decode("QPSK-S_8/9", Y, n_ite=5, early_stop=False)
