@@ -52,6 +52,7 @@ def parse():
     p.add_argument("--e2e-clones", type=int, default=3)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-int16", action="store_true", help="skip the extra fixed-point (int16) line of the same workload")
     p.add_argument("--no-compaction", action="store_true")
     p.add_argument("--rounds", type=int, default=0, help="decoding rounds (frame compaction between rounds); 0 = library default")
     p.add_argument("--exit-eighths", type=int, default=0, help="hand-over threshold in eighths of a group; 0 = library default")
@@ -327,7 +328,8 @@ def main():
                                     "frac": round(msg_bytes_frame * F / (ldpc_ms * 1e-3) / 1e9 / peak, 4)}}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            roofline["traffic"] = json.load(f).get(args.workload + "_" + args.prec)
+            per_frame = json.load(f).get("per_frame", {}).get(args.workload + "_" + args.prec)
+            roofline["traffic"] = None if per_frame is None else int(per_frame * F)  # DRAM bytes of the LDPC launches of a step
     except Exception:
         pass
     stage_ms = {k[:-3]: round(tm[k] / max(1, tm[k[:-3] + "_calls"]), 4) for k in tm if k.endswith("_ms") and tm[k[:-3] + "_calls"]}
@@ -424,6 +426,29 @@ def main():
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "Mbit/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
 
+    # ---- the same workload through the fixed-point (int16, bit-exact vs AFF3CT's int16 decoder) kernel, device-resident only:
+    # a separate process after this one released its HBM (N = 1 runs only; the headline stays the float path the dvbs2
+    # binaries run)
+    int16 = None
+    if rank == 0 and world == 1 and args.prec == "f32" and not args.no_int16:
+        h.close()
+        h = None
+        del batches, V, chain, tx, sig, rx  # sig / rx: the loop variables still hold the last input batch
+        torch.cuda.empty_cache()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--prec", "i16", "--workload", args.workload,
+                                "--ite", str(args.ite), "--steps", str(max(3, args.steps // 2)), "--warmup", "3", "--no-e2e",
+                                "--no-cpu", "--no-int16"] + (["--ebn0", str(args.ebn0)] if args.ebn0 is not None else []),
+                               capture_output=True, text=True, timeout=600)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            int16 = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
+                     "frames_per_step_per_gpu": d["config"]["frames_per_step_per_gpu"], "stage_ms": d["stage_ms"],
+                     "quantizer": "Quantizer_pow2 6 bits, 2 fractional (AFF3CT LDPC defaults)",
+                     "message_passing": d["roofline"]["message_passing"], "mean_iterations": d["fer"]["mean_iterations"],
+                     "ldpc_fer": d["fer"]["ldpc_fer"], "bch_fer": d["fer"]["bch_fer"], "gpu_launches": d["gpu_launches"]}
+        except Exception as e:  # noqa: BLE001
+            int16 = {"value": None, "error": repr(e)[:300]}
+
     if rank == 0:
         out = {
             "metric": "info Mbit/s, %s NMS %d-iter decode chain (demap+LDPC+BCH)" % (modcod, args.ite),
@@ -435,14 +460,15 @@ def main():
                        "l2": "inputs %.1f GB per step >> 126 MB L2, %d batches rotated" % (F * 2 * n_sym * 4 / 1e9, NB),
                        "parallelism": "frames sharded by batch, %d rank(s), no data-path collective" % world},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "stage_ms": stage_ms,
+            "stage_ms": stage_ms, "int16": int16,
             "fer": {"frames": int(cnt[0]), "ldpc_fer": cnt[2] / max(1, cnt[0]), "bch_fer": cnt[3] / max(1, cnt[0]),
                     "mean_iterations": cnt[1] / max(1, cnt[0]),
                     "monitor": {"frames": int(mon[0]), "bit_errors": int(mon[1]), "frame_errors": int(mon[2]),
                                 "fer": mon[2] / max(1, mon[0]), "ber": mon[1] / max(1, mon[0] * K_bch)}},
         }
         print(json.dumps(out))
-    h.close()
+    if h is not None:
+        h.close()
     if world > 1:
         dist.destroy_process_group()
 

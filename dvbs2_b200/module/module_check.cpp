@@ -28,11 +28,14 @@
 #include "Module/Decoder_BCH_DVBS2/Decoder_BCH_DVBS2.hpp"
 #include "Module/Encoder_BCH_DVBS2/Encoder_BCH_DVBS2.hpp"
 #include "Module/Scrambler/Scrambler_BB/Scrambler_BB.hpp"
+#include "Module/Framer/Framer.hpp"
+#include "Module/Estimator/Estimator_DVBS2.hpp"
 
 #include "Decoder_BCH_DVBS2_cuda.hpp"
 #include "Decoder_LDPC_DVBS2_cuda.hpp"
 #include "Decoder_chain_DVBS2_cuda.hpp"
 #include "Modem_DVBS2_cuda.hpp"
+#include "Receiver_chain_DVBS2_cuda.hpp"
 
 using namespace aff3ct;
 
@@ -361,11 +364,59 @@ main(int argc, char** argv)
                "fused GPU module: FE agrees with the all-CPU chain (its own demapper) up to LLR rounding");
         expect(cnt->accepted_wrong.load() == 0 || cpu_fe > 0, "BCH-accepted frames carry the payload");
 
+        // ------------------------------------------------------------------ receiver stage from PL frames (main.cpp:86-92)
+        long rx_be = 0, rx_fe = 0, rxc_be = 0, rxc_fe = 0;
+        double sig_rel = 0;
+        {
+            const int n_sym = N / mc.bps, pl_sym = 90 * (n_sym / 90 + 1) + 36 * (n_sym / 1440);
+            module::Framer<float> framer(2 * n_sym, 2 * pl_sym, modcod, P);
+            module::Estimator_DVBS2<float> est(2 * n_sym, (float)mc.K_bch / (float)N, mc.bps, P);
+            std::vector<float> plf((size_t)P * 2 * pl_sym), xfec((size_t)P * 2 * n_sym), sg(P), eb(P), es(P), li((size_t)P * N),
+              ln((size_t)P * N);
+            std::vector<int> v1((size_t)P * mc.N_bch), v2((size_t)P * mc.K_bch), d2((size_t)P * mc.K_bch);
+            std::vector<int8_t> c1(P), c2(P);
+            framer.generate(pool->sym, plf);
+            // all-CPU: remove_plh -> estimate -> demodulate -> deinterleave -> LDPC -> BCH -> descramble
+            framer.remove_plh(plf, xfec);
+            est.estimate(xfec, sg, eb, es);
+            mdm.demodulate(sg, xfec, li);
+            itl_f.deinterleave(li, ln);
+            ldpc_seq.decode_siho(ln.data(), c1.data(), v1.data());
+            bch.decode_hiho(v1.data(), c2.data(), v2.data());
+            scr.descramble(v2, d2);
+            expect(xfec == pool->sym, "reference Framer: remove_plh(generate(x)) == x");
+            dvbs2_b200::Receiver_chain_DVBS2_cuda g_rx(modcod, 10, "NMS", 1.f, true, P);
+            std::vector<float> g_sig(P);
+            std::vector<int> g_v((size_t)P * mc.K_bch);
+            std::vector<int8_t> g_c1(P), g_c2(P);
+            using namespace dvbs2_b200;
+            g_rx[rcv::sck::receive::Y_N1].bind(plf);
+            g_rx[rcv::tsk::receive].exec();
+            std::copy_n(static_cast<float*>(g_rx[rcv::sck::receive::SIG].get_dataptr()), P, g_sig.begin());
+            std::copy_n(static_cast<int32_t*>(g_rx[rcv::sck::receive::V_K].get_dataptr()), (size_t)P * mc.K_bch, g_v.begin());
+            std::copy_n(static_cast<int8_t*>(g_rx[rcv::sck::receive::CWD_bch].get_dataptr()), P, g_c2.begin());
+            for (int f = 0; f < P; f++)
+            {
+                sig_rel = std::max(sig_rel, (double)std::fabs(g_sig[f] - sg[f]) / sg[f]);
+                long e = 0, ec = 0;
+                for (int i = 0; i < mc.K_bch; i++)
+                {
+                    e += g_v[(size_t)f * mc.K_bch + i] != pool->U[(size_t)f * mc.K_bch + i];
+                    ec += d2[(size_t)f * mc.K_bch + i] != pool->U[(size_t)f * mc.K_bch + i];
+                }
+                rx_be += e, rx_fe += e != 0, rxc_be += ec, rxc_fe += ec != 0;
+                if (g_c2[f] && c2[f]) expect(e == 0 && ec == 0, "receiver stage: frames both BCH decoders accept carry the payload");
+            }
+            expect(sig_rel <= 1e-5, "Receiver_chain_DVBS2_cuda: sigma within 1e-5 of Estimator_DVBS2");
+            expect(rx_fe == rxc_fe || std::labs(rx_fe - rxc_fe) <= 1 + rxc_fe / 10,
+                   "Receiver_chain_DVBS2_cuda: FE agrees with the all-CPU receiver stage up to LLR rounding");
+        }
+
         printf("{\"modcod\": \"%s\", \"frames\": %d, \"demod_max_rel_err\": %.3g, \"ldpc_fe_cpu\": %d, \"bch_fe_cpu\": %ld, "
                "\"seq_frames\": %ld, \"seq_be\": %ld, \"seq_fe\": %ld, \"ref_be\": %ld, \"ref_fe\": %ld, \"cpu_be\": %ld, \"cpu_fe\": %ld, "
-               "\"failures\": %d}\n",
+               "\"rx_stage_sigma_rel\": %.3g, \"rx_stage_fe\": %ld, \"rx_stage_fe_cpu\": %ld, \"failures\": %d}\n",
                modcod.c_str(), P, max_rel, (int)std::count(c_seq.begin(), c_seq.end(), 0), cpu_fe, cnt->frames.load(),
-               cnt->be.load(), cnt->fe.load(), ref_be, ref_fe, cpu_be, cpu_fe, failures);
+               cnt->be.load(), cnt->fe.load(), ref_be, ref_fe, cpu_be, cpu_fe, sig_rel, rx_fe, rxc_fe, failures);
     }
     catch (const std::exception& e)
     {

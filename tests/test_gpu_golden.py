@@ -99,3 +99,27 @@ def test_bch_stress_vectors_vs_reference_outputs():
         Decoder_BCH_DVBS2_cuda(h, F).decode_hiho(Y, cwd, V)
         assert np.array_equal(cwd, g["cwd_%d" % K]) and np.array_equal(V, ub(g["V_%d" % K], K))
         h.close()
+
+
+@pytest.mark.parametrize("modcod", ALL)
+def test_framer_and_estimator_vs_reference_outputs(modcod):
+    """remove_plh and Estimator_DVBS2 on the device against the compiled reference's outputs (rx_front.npz)."""
+    import hashlib
+
+    from dvbs2_b200 import Estimator_DVBS2_cuda, Framer_DVBS2_cuda, Handle
+
+    g = np.load(os.path.join(GOLD, "rx_front.npz"))
+    k, mc = modcod.replace("/", "_"), MODCODS[modcod]
+    n_sym = N_LDPC // mc["bps"]
+    pl = np.ascontiguousarray(g[k + "_pl"])
+    F = pl.shape[0]
+    h = Handle(modcod=modcod, n_frames=F)
+    x = np.zeros((F, 2 * n_sym), np.float32)
+    Framer_DVBS2_cuda(h, F).remove_plh(pl, x)
+    assert hashlib.sha256(x.tobytes()).digest() == g[k + "_xfec_sha"].tobytes()
+    sig, eb, es = (np.zeros(F, np.float32) for _ in range(3))
+    Estimator_DVBS2_cuda(h, F).estimate(x, sig, eb, es)
+    ref = g[k + "_est"]
+    assert np.max(np.abs(sig - ref[0]) / ref[0]) < 5e-6
+    assert np.allclose(eb, ref[1], rtol=0, atol=2e-4) and np.allclose(es, ref[2], rtol=0, atol=2e-4)
+    h.close()

@@ -138,3 +138,22 @@ def test_nms_075_bpsk_curve_of_the_reference(oracle):
         assert abs(p - p_ref) <= 4 * sd, (ebn0, p, p_ref, sd)
         # decoded words of converged frames are the transmitted ones
         assert np.array_equal(V[cwd == 1], U[cwd == 1])
+
+
+@pytest.mark.parametrize("modcod", ALL)
+def test_framer_and_estimator_match_reference(oracle, modcod):
+    """SURVEY §8f N1: oracle_remove_plh == Framer::remove_plh (exact) and oracle_estimate == Estimator_DVBS2::estimate (the
+    compiled reference contracts a*a + b*b into FMAs, hence 3e-6 relative) on PL frames made by the reference's Framer::generate
+    (tests/golden/make_golden_rx_front.py)."""
+    g = np.load(os.path.join(GOLD, "rx_front.npz"))
+    k, mc = modcod.replace("/", "_"), MODCODS[modcod]
+    n_sym = N_LDPC // mc["bps"]
+    pl = g[k + "_pl"]
+    assert pl.shape[1] == 2 * oracle.pl_frame_symbols(n_sym)
+    x = oracle.remove_plh(n_sym, pl)
+    assert hashlib.sha256(np.ascontiguousarray(x).tobytes()).digest() == g[k + "_xfec_sha"].tobytes()
+    assert np.array_equal(oracle.remove_plh(n_sym, oracle.insert_plh(n_sym, x)), x)
+    sig, eb, es = oracle.estimate(n_sym, mc["K_bch"], mc["bps"], x)
+    ref = g[k + "_est"]
+    assert np.max(np.abs(sig - ref[0]) / ref[0]) < 3e-6
+    assert np.allclose(eb, ref[1], rtol=0, atol=1e-4) and np.allclose(es, ref[2], rtol=0, atol=1e-4)

@@ -94,3 +94,20 @@ def test_bch(oracle, ref, K, N):
     Vr, cr = ref.bch_decode(K, N, Y)
     assert np.array_equal(cwd, cr) and np.array_equal(V, Vr)
     assert np.array_equal(oracle.bb_scramble(K, V), ref.descramble(K, V))
+
+
+@pytest.mark.parametrize("modcod", ["QPSK-S_8/9", "QPSK-S_3/5", "8PSK-S_3/5", "8PSK-S_8/9", "16APSK-S_8/9"])
+def test_framer_and_estimator(oracle, ref, modcod):
+    """Framer::remove_plh (exact) and Estimator_DVBS2::estimate (FMA contraction in the compiled reference: 3e-6)."""
+    from oracle.oracle import MODCODS, N_LDPC, synth_frames
+
+    mc = MODCODS[modcod]
+    n_sym = N_LDPC // mc["bps"]
+    pl_sym = oracle.pl_frame_symbols(n_sym)
+    s = synth_frames(oracle, modcod, 5, 5.0, seed=3)
+    pl = ref.framer_generate(modcod, n_sym, pl_sym, s["rx"])
+    a, b = oracle.remove_plh(n_sym, pl), ref.remove_plh(modcod, n_sym, pl_sym, pl)
+    assert np.array_equal(a, b) and np.array_equal(a, s["rx"])
+    eo, er = oracle.estimate(n_sym, mc["K_bch"], mc["bps"], a), ref.estimate(n_sym, mc["K_bch"], mc["bps"], a)
+    assert np.max(np.abs(eo[0] - er[0]) / er[0]) < 3e-6
+    assert np.allclose(eo[1], er[1], rtol=0, atol=1e-4) and np.allclose(eo[2], er[2], rtol=0, atol=1e-4)
