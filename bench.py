@@ -240,6 +240,10 @@ def main():
         per_frame = 1.6 * (N_LDPC * esz0 + (N_LDPC - N_bch) * (8 if args.prec == "i16" else 16) + N_LDPC // 4) + NB * (2 * n_sym * 4 + 4) + K_bch * 4 + 16
         free_b = torch.cuda.mem_get_info(dev)[0]
         F = next((k * wave for k in (3, 2) if k * wave * per_frame < 0.7 * free_b), wave)
+        if world > 1:  # every rank decodes the same number of frames per step (weak scaling): agree on the smallest
+            t = torch.tensor([F], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            F = int(t.item())
 
     tune = dict(compaction=not args.no_compaction, compaction_rounds=args.rounds, compaction_exit_eighths=args.exit_eighths,
                 compaction_nf_later=args.nf_later)

@@ -191,7 +191,7 @@ struct CheckRegs
 template<typename R, int DI, int NF, bool PK = false>
 __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const LdpcLaunch a)
 {
-    static_assert(!PK || (sizeof(R) == 2 && NF == 4), "packed pairs: int16_t, four frames per lane");
+    static_assert(!PK || (sizeof(R) == 2 && (NF == 4 || NF == 2)), "packed pairs: int16_t, two or four frames per lane");
     using A = Arith<R>;
     using C = typename A::C;
     using Raw = typename RawVec<sizeof(R) * NF>::T;
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
 
             if constexpr (PK)
             {
-                constexpr int NP = 2;         // pairs per lane
+                constexpr int NP = NF / 2;    // pairs per lane (2 in round 1; 1 in the narrower groups of the later rounds)
                 constexpr uint32_t ONE = 0x00010001u, MAXV = 0x7fff7fffu;
                 uint4* __restrict__ cnp = a.cn + (size_t)g * M * NP * 32 + lane; // [c][pair][lane]
                 const bool have_state = resumed || ite > 0;
@@ -281,7 +281,10 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
                 auto load_var = [&](int c, int i) { // i < DI: i-th information variable of check c;  i == DI + 1: var[K + c]
                     unsigned vi = (unsigned)(K + c);
                     if (i < DI) vi = (s_idx[c * IW + (i >> 1)] >> ((i & 1) * 16)) & 0xffffu;
-                    x[i] = __ldcg(reinterpret_cast<const uint2*>(vbytes + (vi * VB + loff)));
+                    if constexpr (NP == 2)
+                        x[i] = __ldcg(reinterpret_cast<const uint2*>(vbytes + (vi * VB + loff)));
+                    else
+                        x[i].x = __ldcg(reinterpret_cast<const uint32_t*>(vbytes + (vi * VB + loff)));
                 };
                 auto load_state = [&](int c) {
 #pragma unroll
@@ -298,11 +301,12 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
                     const uint32_t* row = s_idx + c * IW;
                     const uint32_t lastm = s_last[c];
                     const bool more = c + 1 < M;
-                    uint32_t min1[NP], c1[NP], c2[NP], sacc[NP];
+                    uint32_t c1[NP], c2[NP], sacc[NP], F0[NP], F1[NP], nidx[NP];
 #pragma unroll
                     for (int p = 0; p < NP; p++)
                     {
                         const uint32_t o1 = rst[p].x, o2 = rst[p].y, S0 = rst[p].z, S1 = rst[p].w;
+                        uint32_t ia = 0, ib = 0; // an edge attaining min1, per half (the last one; any will do, see header)
                         const uint32_t no1 = pk::neg(o1), no2 = pk::neg(o2);
                         const uint32_t ohA = 1u << ((S1 >> 11) & 31u), ohB = 1u << (S1 >> 27);
                         const uint32_t E0 = __byte_perm(ohA, ohB, 0x5410), E1 = __byte_perm(ohA, ohB, 0x7632);
@@ -323,9 +327,17 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
                             const uint32_t ab = pk::absv(ti);
                             sa ^= ti;
                             m2 = pk::vmin(m2, pk::vmax(ab, m1));
-                            m1 = pk::vmin(m1, ab);
+                            bool ph, pl;
+                            m1 = __vibmin_s16x2(ab, m1, &ph, &pl); // min + "ab <= m1" per half in one VIMNMX
+                            ia = pl ? (uint32_t)i : ia;
+                            ib = ph ? (uint32_t)i : ib;
                         }
-                        min1[p] = m1, sacc[p] = sa;
+                        sacc[p] = sa;
+                        nidx[p] = ia | (ib << 16);
+                        { // one-hot masks of those edges in the sign-word arrangement (edges 0..15 / 16.., first | second frame)
+                            const uint32_t ha = 1u << ia, hb = 1u << ib;
+                            F0[p] = __byte_perm(ha, hb, 0x5410), F1[p] = __byte_perm(ha, hb, 0x7632);
+                        }
                         uint32_t n2 = m2, n1 = m1;
                         if (a.k8 != 8)
                         { // Update_rule_NMS.hxx:14-39, per half
@@ -336,10 +348,10 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
                     }
                     if (more) load_state(c + 1);
 
-                    uint32_t ns0[NP], ns1[NP], nidx[NP];
+                    uint32_t ns0[NP], ns1[NP];
 #pragma unroll
                     for (int p = 0; p < NP; p++)
-                        ns0[p] = ns1[p] = nidx[p] = 0;
+                        ns0[p] = ns1[p] = 0;
 #pragma unroll
                     for (int i = 0; i < D; i++)
                     {
@@ -348,14 +360,14 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
 #pragma unroll
                         for (int p = 0; p < NP; p++)
                         {
-                            uint32_t ti = p == 0 ? x[i].x : x[i].y;
-                            asm volatile("" : "+r"(ti)); // |t| is recomputed here, not kept in registers since pass 1
-                            const uint32_t em = pk::zeromask(pk::absv(ti) ^ min1[p]); // |t| == min1
-                            const uint32_t xs = sacc[p] ^ ti;                         // bits 15 / 31: sign of the new message
-                            const uint32_t sm = pk::signmask(xs), s1 = (xs >> 15) & ONE;
+                            const uint32_t ti = p == 0 ? x[i].x : x[i].y;
+                            // the edge that attained min1 gets the magnitude built from min2 (with ties min2 = min1, so every
+                            // edge with |t| == min1 gets the same value, as Update_rule_MS.hxx:82-92 demands)
+                            const uint32_t em = pk::bitmask(i < 16 ? F0[p] : F1[p], b);
+                            const uint32_t xs = sacc[p] ^ ti; // bits 15 / 31: sign of the new message
+                            const uint32_t sm = pk::signmask(xs), s1 = sm & ONE;
                             // t + sign * mag with -mag = (mag ^ 0xffff) + 1 per half
                             nv[p] = pk::add(pk::add(ti, pk::mux(c1[p], c2[p], em) ^ sm), s1);
-                            nidx[p] = pk::mux((uint32_t)i * ONE, nidx[p], em);
                             const uint32_t sb = s1 << b;
                             if (i < 16)
                                 ns0[p] |= sb;
@@ -385,15 +397,25 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
                             vi = K + c;
                             ballot = true;
                         }
-                        if (mine_any) __stcg(reinterpret_cast<uint2*>(vbytes + (vi * VB + loff)), make_uint2(nv[0], nv[1]));
+                        if (mine_any)
+                        {
+                            if constexpr (NP == 2)
+                                __stcg(reinterpret_cast<uint2*>(vbytes + (vi * VB + loff)), make_uint2(nv[0], nv[NP - 1]));
+                            else
+                                __stcg(reinterpret_cast<uint32_t*>(vbytes + (vi * VB + loff)), nv[0]);
+                        }
                         if (ballot) // warp-uniform: only the last update of a variable in the iteration fixes its hard decision
                         {
-                            uint4 hw;
-                            hw.x = __ballot_sync(FULL, (nv[0] & 0x8000u) != 0);
-                            hw.y = __ballot_sync(FULL, (int)nv[0] < 0);
-                            hw.z = __ballot_sync(FULL, (nv[1] & 0x8000u) != 0);
-                            hw.w = __ballot_sync(FULL, (int)nv[1] < 0);
-                            if (lane == 0) __stcg(reinterpret_cast<uint4*>(hd + (size_t)vi * NF), hw);
+                            uint32_t hww[NF];
+#pragma unroll
+                            for (int p = 0; p < NP; p++)
+                            {
+                                hww[2 * p] = __ballot_sync(FULL, (nv[p] & 0x8000u) != 0);
+                                hww[2 * p + 1] = __ballot_sync(FULL, (int)nv[p] < 0);
+                            }
+                            HdVec hw;
+                            memcpy(&hw, hww, sizeof(HdVec));
+                            if (lane == 0) __stcg(reinterpret_cast<HdVec*>(hd + (size_t)vi * NF), hw);
                         }
                     }
 #pragma unroll
@@ -772,7 +794,7 @@ __global__ void __launch_bounds__(128) compact_copy_kernel(const CompactLaunch c
     const int c0 = (int)((long)c.M * part / COMPACT_PARTS), c1 = (int)((long)c.M * (part + 1) / COMPACT_PARTS);
     if constexpr (sizeof(R) == 2)
     { // packed pairs (ldpc_decode_kernel<int16_t, ., 4, true>): state [check][pair][lane], one half of every word per frame
-        static_assert(NF == 4 && ND == 4, "int16_t groups hold four frames per lane");
+        static_assert((NF == 4 || NF == 2) && (ND == 4 || ND == 2), "int16_t groups hold two or four frames per lane");
         size_t pbase[ND];
         int sh[ND];
 #pragma unroll
@@ -795,13 +817,13 @@ __global__ void __launch_bounds__(128) compact_copy_kernel(const CompactLaunch c
                 {
                     const int j = 2 * p + hf;
                     if (!valid[j]) continue;
-                    const uint4 x = __ldcg(c.cn_src + pbase[j] + (size_t)k * 2 * 32);
+                    const uint4 x = __ldcg(c.cn_src + pbase[j] + (size_t)k * (NF / 2) * 32);
                     w[0] |= ((x.x >> sh[j]) & 0xffffu) << (16 * hf);
                     w[1] |= ((x.y >> sh[j]) & 0xffffu) << (16 * hf);
                     w[2] |= ((x.z >> sh[j]) & 0xffffu) << (16 * hf);
                     w[3] |= ((x.w >> sh[j]) & 0xffffu) << (16 * hf);
                 }
-                cd[(size_t)(k * 2 + p) * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+                cd[(size_t)(k * (ND / 2) + p) * 32] = make_uint4(w[0], w[1], w[2], w[3]);
             }
     }
     else
@@ -981,7 +1003,7 @@ launch_ldpc_decode(const LdpcLaunch& a, int precision, cudaStream_t s)
     switch (precision)
     {
         case 0: return a.nf == 1 ? launch_ldpc_t<float, 1>(a, s) : launch_ldpc_t<float, 2>(a, s);
-        case 1: return launch_ldpc_t<int16_t, 4, true>(a, s);
+        case 1: return a.nf == 2 ? launch_ldpc_t<int16_t, 2, true>(a, s) : launch_ldpc_t<int16_t, 4, true>(a, s);
         case 2: return launch_ldpc_t<int8_t, 4>(a, s);
     }
     return cudaErrorInvalidValue;
@@ -1001,9 +1023,10 @@ launch_compact_t(const CompactLaunch& c, cudaStream_t s)
 int
 ldpc_later_frames_per_lane(int precision, int preferred)
 {
-    // float: narrower groups in the later rounds (their few warps are latency-bound, so halving the work per check
-    // halves the time a warp needs per check) unless asked otherwise; integers keep their 4-byte lanes
+    // float and int16: narrower groups in the later rounds (their few warps are latency-bound, so halving the work per
+    // check halves the time a warp needs per check) unless asked otherwise; int8 keeps its 4-byte lanes
     if (precision == 0) return preferred == 2 ? 2 : 1;
+    if (precision == 1) return preferred == 4 ? 4 : 2;
     return ldpc_frames_per_lane(precision);
 }
 
@@ -1020,6 +1043,8 @@ launch_compact(const CompactLaunch& c, int precision, cudaStream_t s)
             break;
         case 1:
             if (c.nf == 4 && c.nf_dst == 4) return launch_compact_t<int16_t, 4, 4>(c, s);
+            if (c.nf == 4 && c.nf_dst == 2) return launch_compact_t<int16_t, 4, 2>(c, s);
+            if (c.nf == 2 && c.nf_dst == 2) return launch_compact_t<int16_t, 2, 2>(c, s);
             break;
         case 2:
             if (c.nf == 4 && c.nf_dst == 4) return launch_compact_t<int8_t, 4, 4>(c, s);

@@ -81,7 +81,7 @@ extern "C"
         int compaction_rounds;       /* decoding rounds incl. the first, 2..4 (0 = default 2)                       */
         int compaction_exit_eighths; /* a group hands its live frames over once fewer than this many eighths of its
                                         frames still iterate, 1..6 (0 = default 4)                                   */
-        int compaction_nf_later;     /* f32 only: frames per lane in rounds >= 2, 1 or 2 (0 = default 1)            */
+        int compaction_nf_later;     /* frames per lane in rounds >= 2: f32 1 or 2 (0 = 1), int16 2 or 4 (0 = 2)   */
         int reserved[3]; /* must be 0                                                                      */
     } dvbs2_cuda_cfg;
 
