@@ -47,9 +47,9 @@ def parse():
     p.add_argument("--ebn0", type=float, default=None)
     p.add_argument("--prec", default="f32", choices=["f32", "i16", "i8"])
     p.add_argument("--ite", type=int, default=10)
-    p.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the largest of 3, 2, 1 waves of the LDPC kernel = SMs x 12 warps x 64 frames each that fits in 70 %% of the free HBM)")
+    p.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the largest of 3, 2, 1 waves of the LDPC kernel = SMs x 12 warps x 64 frames each that fits in 80 %% of the free HBM)")
     p.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e step per GPU (default: one wave)")
-    p.add_argument("--e2e-clones", type=int, default=3)
+    p.add_argument("--e2e-clones", type=int, default=4)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-int16", action="store_true", help="skip the extra fixed-point (int16) line of the same workload")
@@ -239,7 +239,7 @@ def main():
         esz0 = {"f32": 4, "i16": 2, "i8": 1}[args.prec]
         per_frame = 1.6 * (N_LDPC * esz0 + (N_LDPC - N_bch) * (8 if args.prec == "i16" else 16) + N_LDPC // 4) + NB * (2 * n_sym * 4 + 4) + K_bch * 4 + 16
         free_b = torch.cuda.mem_get_info(dev)[0]
-        F = next((k * wave for k in (3, 2) if k * wave * per_frame < 0.7 * free_b), wave)
+        F = next((k * wave for k in (3, 2) if k * wave * per_frame < 0.8 * free_b), wave)
         if world > 1:  # every rank decodes the same number of frames per step (weak scaling): agree on the smallest
             t = torch.tensor([F], dtype=torch.int64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MIN)

@@ -463,10 +463,12 @@ chunk_frames(const dvbs2_cuda_handle* h, int n_frames)
     // one chunk per pipeline stream: the LDPC kernel's duration hardly depends on the chunk size (a warp walks its group
     // through every check either way), so fewer, larger chunks keep more SMs busy while copies of the other chunks — and
     // of other module clones — proceed
+    // ... but not below four groups per SM: a launch with fewer groups runs one or two warps per SM at the latency of a
+    // full one (measured: 12 chunks of 148 groups each took as long as the PCIe traffic they were meant to hide), so calls
+    // of up to n_sms * 4 groups are not split at all and rely on the other module clones for overlap
     int per = (n_frames + N_PIPE - 1) / N_PIPE;
-    per = std::max(per, 2048);
+    per = std::max(per, h->n_sms * 4 * 32 * h->nf);
     per = (per + 255) / 256 * 256; // whole decoder groups for every precision
-    (void)h;
     return per;
 }
 } // namespace

@@ -141,38 +141,43 @@ struct LaneVec<int8_t, 4>
     }
 };
 
-// warp = (decoder group of 32*NF frames, 16 consecutive symbols); lane l demaps frames l, 32+l, ... of the group.
-// Symbols are staged through shared memory so the global reads are 128-byte rows of one frame and every global write
-// is one full row var[group][v][0..31][0..NF-1] of the decoder's layout (256 B for float).
+// warp = (decoder group of 32*NF frames, SYMS consecutive symbols); lane l demaps frames l, 32+l, ... of the group.
+// Symbols are staged through shared memory so the global reads are 128-byte (SYMS = 16) or 64-byte (SYMS = 8, two frames per
+// warp load) rows of one frame and every global write is one full row var[group][v][0..31][0..NF-1] of the decoder's layout
+// (256 B for float and int16).  Four-frame lanes use the shorter tile so that as many warps fit on an SM (shared memory).
 template<int NF>
 struct DemapCfg
 {
-    static constexpr int WARPS = 8 / NF; // 33.8 KB of shared memory per block for every NF
+    static constexpr int SYMS = NF == 4 ? 8 : 16;        // symbols per warp tile
+    static constexpr int WARPS = NF == 1 ? 8 : 4;        // <= 34.8 KB of shared memory per block
 };
 template<int BPS, typename R, int NF>
 __global__ void __launch_bounds__(DemapCfg<NF>::WARPS * 32) demap_to_var_kernel(const DemapLaunch a, R* __restrict__ var)
 {
-    constexpr int WARPS = DemapCfg<NF>::WARPS;
+    constexpr int WARPS = DemapCfg<NF>::WARPS, SYMS = DemapCfg<NF>::SYMS;
+    constexpr int RPL = 16 / SYMS; // frame rows per warp load: 1 (32 floats per row) or 2 (16 floats per row)
     using Vec = typename LaneVec<R, NF>::T;
     __shared__ float cs[2 << BPS];
-    __shared__ float tile[WARPS][NF][32][33];
+    __shared__ float tile[WARPS][NF][32][2 * SYMS + 1];
     if (threadIdx.x < (2 << BPS)) cs[threadIdx.x] = a.cstl[threadIdx.x];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.y; // decoder group
-    const int k0 = (blockIdx.x * WARPS + warp) * 16;
+    const int k0 = (blockIdx.x * WARPS + warp) * SYMS;
     if (k0 >= a.n_sym) return;
-    // row length and position of symbol k0 in it; a tile of 16 symbols never straddles a pilot block (1440 = 90 * 16)
+    // row length and position of symbol k0 in it; a tile never straddles a pilot block (1440 = 90 * 16)
     const int nfl = a.pl_sym > 0 ? 2 * a.pl_sym : 2 * a.n_sym;
-    const int e = (a.pl_sym > 0 ? 2 * pl_symbol_pos(k0, a.n_sym) : 2 * k0) + lane;
-    const bool in_frame = 2 * k0 + lane < 2 * a.n_sym;
+    const int col = lane % (2 * SYMS), sub = lane / (2 * SYMS);
+    const int e = (a.pl_sym > 0 ? 2 * pl_symbol_pos(k0, a.n_sym) : 2 * k0) + col;
+    const bool in_frame = 2 * k0 + col < 2 * a.n_sym;
 #pragma unroll
     for (int j = 0; j < NF; j++)
 #pragma unroll 16
-        for (int r = 0; r < 32; r++)
+        for (int r0 = 0; r0 < 32; r0 += RPL)
         {
+            const int r = r0 + sub;
             const int f = (g * NF + j) * 32 + r;
-            tile[warp][j][r][lane] = (f < a.n_frames && in_frame) ? __ldg(a.sym + (size_t)f * nfl + e) : 0.f;
+            tile[warp][j][r][col] = (f < a.n_frames && in_frame) ? __ldg(a.sym + (size_t)f * nfl + e) : 0.f;
         }
     __syncwarp();
     float inv[NF];
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(DemapCfg<NF>::WARPS * 32) demap_to_var_kernel(
     const float vmax = (float)((1 << (a.quant_bits - 1)) - 1);
     Vec* vg = reinterpret_cast<Vec*>(var) + (size_t)g * N_LDPC * 32 + lane;
 #pragma unroll 2
-    for (int s = 0; s < 16; s++)
+    for (int s = 0; s < SYMS; s++)
     {
         const int k = k0 + s;
         if (k >= a.n_sym) break;
@@ -316,7 +321,7 @@ demap_to_var_launch(const DemapLaunch& a, void* var, cudaStream_t s)
 {
     constexpr int WARPS = DemapCfg<NF>::WARPS;
     const int groups = (a.n_frames + 32 * NF - 1) / (32 * NF); // whole decoder groups: pad frames get zeros
-    const dim3 grid((a.n_sym + 16 * WARPS - 1) / (16 * WARPS), groups);
+    const dim3 grid((a.n_sym + DemapCfg<NF>::SYMS * WARPS - 1) / (DemapCfg<NF>::SYMS * WARPS), groups);
     demap_to_var_kernel<BPS, R, NF><<<grid, WARPS * 32, 0, s>>>(a, (R*)var);
 }
 

@@ -27,6 +27,7 @@
 //   * Groups are handed to warps through an atomic queue (persistent CTAs, one per SM).
 // The kernel is HBM-bound on message passing: bytes per frame and iteration = 2*sizeof(R)*(E_info + M) + 32*M
 // (DESIGN.md §5).
+#include <algorithm>
 #include <cfloat>
 #include <cstdint>
 #include <cstring>
@@ -984,7 +985,10 @@ launch_ldpc_k(const LdpcLaunch& a, cudaStream_t s)
     // spread the groups over all SMs (a warp's walk through the checks is latency-bound, so 4 warps on each of 148 SMs
     // finish sooner than 12 warps on each of 50); the queue hands groups to whichever warp is free
     const int blocks = groups < a.n_sms ? groups : a.n_sms;
-    k<<<blocks, LDPC_WARPS * 32, smem, s>>>(a);
+    // ... and a CTA carries only the warps it can feed, so that launches of other streams (pipeline chunks, other module
+    // clones) fit beside it on the SM instead of waiting for a mostly idle 12-warp CTA to drain
+    const int warps = std::min(LDPC_WARPS, std::max(1, (groups + blocks - 1) / std::max(1, blocks)));
+    k<<<blocks, warps * 32, smem, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -5,7 +5,7 @@
  * reference file:line it follows.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline
  * leg may load it; the product (libdvbs2_cuda) never links or calls it.
  *
- * Parity status: PINNED — tests/test_oracle_vs_ref.py checks every function below bit-for-bit
+ * Parity status: PINNED — tests/test_oracle_vs_reference.py checks every function below bit-for-bit
  * (demapper: to float rounding) against the compiled, unmodified reference (oracle/_ref/libdvbs2_ref.so,
  * built by oracle/build_ref.sh) and tests/golden/ holds vectors generated from that reference.
  *

@@ -1,0 +1,25 @@
+#!/usr/bin/env bash
+cd "${GRAFT_REPO_ROOT:-.}"
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_bch_demod_chain.py tests/test_gpu_fer_curve.py tests/test_gpu_rx_front.py -q -m gpu -x 2>&1 | tail -12
+: > gpurun_out/exp_q.jsonl
+run() { echo "## $*" >> gpurun_out/exp_q.jsonl; timeout 300 python bench.py --no-cpu --no-int16 --steps 6 --warmup 3 --frames 113664 "$@" >> gpurun_out/exp_q.jsonl 2>> gpurun_out/exp_q.err; }
+run --e2e-clones 3
+run --e2e-clones 2
+run --e2e-clones 4
+run --e2e-clones 3 --e2e-frames 227328
+run --e2e-clones 6 --e2e-frames 227328
+python - <<'PY'
+import json
+for line in open("gpurun_out/exp_q.jsonl"):
+    if line.startswith("##"):
+        print(line.strip(), end="  ->  ")
+    else:
+        try:
+            d = json.loads(line)
+            e = d["e2e"]
+            print(e["value"], e["ms_per_step"], e["frames_per_step_per_gpu"], "packed", e["packed_output"]["value"], e["matches_device_path"])
+        except Exception as ex:
+            print("bad line", line[:200])
+PY
+tail -5 gpurun_out/exp_q.err

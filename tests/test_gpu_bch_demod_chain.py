@@ -221,11 +221,12 @@ def test_packed_output_format(oracle, modcod, ebn0, F):
 
 
 def test_chain_full_size_round_trip(oracle):
-    """BASELINE-size property test: 8192 frames through the chunked host API; every frame BCH accepts must descramble
-    to its payload, and at 5 dB (well past the waterfall) every frame is accepted."""
+    """BASELINE-size property test: 40960 frames through the chunked host API (two chunks on two pipeline streams: a call is
+    split once it exceeds four groups per SM); every frame BCH accepts must descramble to its payload, and at 5 dB (well past
+    the waterfall) every frame is accepted."""
     from dvbs2_b200 import Decoder_chain_DVBS2_cuda, Handle
 
-    modcod, F0, reps = "QPSK-S_8/9", 64, 128
+    modcod, F0, reps = "QPSK-S_8/9", 64, 640
     mc = MODCODS[modcod]
     s = synth_frames(oracle, modcod, F0, 5.0, seed=41)
     F = F0 * reps
