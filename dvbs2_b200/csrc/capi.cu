@@ -21,6 +21,7 @@ using namespace dvbs2;
 namespace
 {
 constexpr int N_PIPE = 4; // streams used to overlap H2D / compute / D2H in the host-buffer entry points
+constexpr int MAX_ROUNDS = 6; // decoding rounds of one LDPC call (frame compaction between them)
 
 struct DevBuf
 {
@@ -58,6 +59,7 @@ struct dvbs2_cuda_handle
     int nf = 1, n_sms = 148;             // frames per lane of the LDPC kernel (group = 32 * nf frames)
     int k8 = 0;
     size_t elt = 4; // sizeof(R)
+    int nf_cfg = 0; // float only: frames per lane forced by the configuration (0 = chosen per call from the batch size)
     int cn_div = 1; // check state: 16 / cn_div bytes per frame and check (int16 packs two frames into one uint4)
     cudaStream_t stream = nullptr;
     cudaStream_t pipe[N_PIPE] = {};
@@ -189,9 +191,21 @@ prof_mark(dvbs2_cuda_handle* h, cudaStream_t s, int stage)
     return DVBS2_OK;
 }
 
+// Frames per lane of one call.  Float: 32-frame groups (one frame per lane) while the call fits in one wave of them — a warp
+// then needs about half the time per check, which is what bounds a small batch (one call is a chain of n_ite * M dependent
+// checks: 30 ms at -F <= 16384 with 64-frame groups, measured) — and 64-frame groups (256-byte chunks, the bandwidth-efficient
+// shape) above that.  The integer precisions keep their fixed four frames per lane.
+int
+call_nf(const dvbs2_cuda_handle* h, int n_frames)
+{
+    if (h->cfg.precision != DVBS2_PREC_F32) return h->nf;
+    if (h->nf_cfg) return h->nf_cfg;
+    return n_frames <= h->n_sms * LDPC_WARPS * 32 ? 1 : 2;
+}
+
 // `first_frame` is a multiple of the group size 32 * nf; per-frame offsets follow from the layouts in kernels.h
 LdpcLaunch
-ldpc_args(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frames, int8_t* cwd, int32_t* n_iter)
+ldpc_args(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frames, int8_t* cwd, int32_t* n_iter, int nf)
 {
     LdpcLaunch a{};
     a.var = (char*)h->var.p + (size_t)first_frame * N_LDPC * h->elt;
@@ -207,7 +221,8 @@ ldpc_args(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frames, i
     a.n_iter = n_iter;
     a.stats = (unsigned long long*)h->stats.p;
     a.n_frames = n_frames;
-    a.n_groups = (n_frames + 32 * h->nf - 1) / (32 * h->nf);
+    a.n_groups = (n_frames + 32 * nf - 1) / (32 * nf);
+    a.nf = nf;
     a.K = h->mc.N_bch, a.M = h->mc.M, a.d_info = h->mc.d_info;
     a.n_ite = h->cfg.n_ite, a.norm = h->cfg.norm, a.k8 = h->k8, a.early_stop = h->cfg.early_stop;
     a.n_sms = h->n_sms;
@@ -244,7 +259,7 @@ demap_args(dvbs2_cuda_handle* h, const float* d_sigma, const float* d_sym, int n
 // Slot-space offsets of a chunk that starts at frame f0 (a multiple of 256; chunks are >= 2048 frames long except the
 // last): the regions of different chunks must be disjoint because chunks run concurrently on the pipeline streams.
 // A chunk of n frames needs < n * e + 128 slots of region B (e = exit_eighths / 8) and < n * (e + e^2 + e^3) + 384 slots
-// of the later rounds' hd / out_hd / bookkeeping space.
+// of the later rounds' hd / out_hd / bookkeeping space (up to MAX_ROUNDS rounds).
 size_t
 region_b_offset(const dvbs2_cuda_handle* h, int f0)
 {
@@ -255,16 +270,19 @@ region_b_offset(const dvbs2_cuda_handle* h, int f0)
 size_t
 ext_slot_offset(const dvbs2_cuda_handle* h, int f0)
 {
-    const size_t e = h->exit_eighths; // n * (e/8 + e^2/64 + e^3/512), rounded up
-    return (((size_t)f0 * (64 * e + 8 * e * e + e * e * e) + 511) / 512 + 255) / 256 * 256 + (size_t)768 * (f0 / 2048);
+    // n * (e + e^2 + ... + e^(MAX_ROUNDS - 1)) with e = exit_eighths / 8, rounded up, + one group of padding per round and chunk
+    double sum = 0, pw = 1;
+    for (int r = 2; r <= MAX_ROUNDS; r++)
+        pw *= h->exit_eighths / 8.0, sum += pw;
+    return ((size_t)std::ceil((double)f0 * sum) + 255) / 256 * 256 + (size_t)256 * (MAX_ROUNDS - 1) * (f0 / 2048);
 }
 
 // LDPC decode of slots [first_frame, first_frame + n_frames): one round, or several rounds with frame compaction in
 // between (at most h->rounds; a round is worth launching only while the previous one had at least two groups)
 int
-run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frames, int8_t* d_cwd, int32_t* d_nit)
+run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frames, int8_t* d_cwd, int32_t* d_nit, int nf0)
 {
-    LdpcLaunch a = ldpc_args(h, s, first_frame, n_frames, d_cwd, d_nit);
+    LdpcLaunch a = ldpc_args(h, s, first_frame, n_frames, d_cwd, d_nit, nf0);
     const bool multi = h->rounds > 1 && h->ext_cap > 0 && h->cfg.early_stop && h->cfg.n_ite >= 4 && a.n_groups >= 2;
     if (!multi)
     {
@@ -284,8 +302,7 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
     const int n_groups0 = a.n_groups;
 
     // round 1 (in place), then compaction + round r for r = 2..rounds
-    a.nf = h->nf;
-    a.exit_below = 32 * h->nf * h->exit_eighths / 8;
+    a.exit_below = 32 * nf0 * h->exit_eighths / 8;
     a.surv_mask = mask0;
     a.surv_iters = (int*)h->surv_iters.p + first_frame;
     CU(h, launch_ldpc_decode(a, h->cfg.precision, s));
@@ -299,13 +316,13 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
     const int rounds = (h->auto_rounds && n_groups0 < 2 * h->n_sms * LDPC_WARPS) ? 2 : h->rounds;
     for (int r = 2; r <= rounds && prev.n_groups >= 2; r++)
     {
-        const int nf = ldpc_later_frames_per_lane(h->cfg.precision, h->nf_later);
+        const int nf = std::min(nf0, ldpc_later_frames_per_lane(h->cfg.precision, h->nf_later)); // groups never widen
         const int gsz = 32 * nf;
         // every group of the previous round hands over fewer than exit_below frames
         const int cap = (prev.n_groups * (prev.exit_below - 1) + gsz - 1) / gsz * gsz;
         const bool to_b = (r % 2) == 0;
         const size_t vslot = to_b ? vb : (size_t)first_frame;
-        if ((to_b ? (vb - F + cap > (size_t)h->ext_cap) : (cap > n_frames + 32 * h->nf)) || hs - F + cap > (size_t)h->ext_slots)
+        if ((to_b ? (vb - F + cap > (size_t)h->ext_cap) : (cap > n_frames + 32 * nf0)) || hs - F + cap > (size_t)h->ext_slots)
         { // cannot happen by construction; frames already handed over would be lost, so fail loudly
             h->last_error = "frame compaction: region overflow";
             return DVBS2_ERR_INVALID;
@@ -342,7 +359,7 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
         if (last) break;
     }
     MergeLaunch m{};
-    m.surv_mask = mask0, m.final_loc = final_loc, m.out_hd = out_hd0, m.n_groups = n_groups0, m.nf = h->nf;
+    m.surv_mask = mask0, m.final_loc = final_loc, m.out_hd = out_hd0, m.n_groups = n_groups0, m.nf = nf0;
     CU(h, launch_merge_back(m, s));
     h->launches += 1;
     return DVBS2_OK;
@@ -355,10 +372,11 @@ run_ldpc(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const void* d_Y,
 {
     if (n_frames == 0) return DVBS2_OK;
     void* var = (char*)h->var.p + (size_t)first_frame * N_LDPC * h->elt;
+    const int nf = call_nf(h, n_frames);
     TRY(prof_mark(h, s, P_PACK));
-    CU(h, launch_pack_llr(d_Y, var, h->cfg.precision, n_frames, s));
+    CU(h, launch_pack_llr(d_Y, var, h->cfg.precision, n_frames, nf, s));
     TRY(prof_mark(h, s, P_LDPC));
-    TRY(run_ldpc_core(h, s, first_frame, n_frames, d_cwd, d_nit));
+    TRY(run_ldpc_core(h, s, first_frame, n_frames, d_cwd, d_nit, nf));
     TRY(prof_mark(h, s, P_UNPACK));
     CU(h, launch_unpack_bits((uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC, d_VK, N_LDPC, h->mc.N_bch, n_frames, s));
     TRY(prof_mark(h, s, P_END));
@@ -397,9 +415,10 @@ run_chain(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const float* d_
         d_sigma = d_sigma_est;
         h->launches += 1;
     }
-    CU(h, launch_demap_to_var(demap_args(h, d_sigma, d_sym, n_frames, pl_frames), var, h->cfg.precision, h->nf, s));
+    const int nf = call_nf(h, n_frames);
+    CU(h, launch_demap_to_var(demap_args(h, d_sigma, d_sym, n_frames, pl_frames), var, h->cfg.precision, nf, s));
     TRY(prof_mark(h, s, P_LDPC));
-    TRY(run_ldpc_core(h, s, first_frame, n_frames, d_cwd_ldpc, d_nit));
+    TRY(run_ldpc_core(h, s, first_frame, n_frames, d_cwd_ldpc, d_nit, nf));
     TRY(prof_mark(h, s, P_BCH));
     CU(h, launch_bch_decode(bch_args(h, first_frame, n_frames, d_cwd_bch), h->bch, s));
     TRY(prof_mark(h, s, P_UNPACK));
@@ -560,6 +579,9 @@ extern "C"
             if (cfg->quant_dec <= 0 || cfg->quant_bits < 2 || cfg->quant_dec > cfg->quant_bits || cfg->quant_bits > type_bits)
                 return DVBS2_ERR_INVALID; // Quantizer_pow2.cpp:81-122
         }
+        if (cfg->ldpc_frames_per_lane != 0 &&
+            (cfg->precision != DVBS2_PREC_F32 || (cfg->ldpc_frames_per_lane != 1 && cfg->ldpc_frames_per_lane != 2)))
+            return DVBS2_ERR_INVALID;
         int ndev = dvbs2_cuda_device_count();
         if (ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) return DVBS2_ERR_CUDA; // no CPU fallback
 
@@ -570,6 +592,7 @@ extern "C"
         h->k8 = k8;
         h->elt = cfg->precision == DVBS2_PREC_F32 ? 4 : cfg->precision == DVBS2_PREC_I16 ? 2 : 1;
         h->nf = ldpc_frames_per_lane(cfg->precision);
+        h->nf_cfg = cfg->ldpc_frames_per_lane; // float only (validated above): 1 or 2 in round 1; 0 = per call from the batch size
         h->cn_div = cfg->precision == DVBS2_PREC_I16 ? 2 : 1;
         h->max_frames = (cfg->max_frames + 32 * h->nf - 1) / (32 * h->nf) * (32 * h->nf);
         h->max_groups = h->max_frames / 32;
@@ -638,12 +661,12 @@ extern "C"
 
         const size_t G = (size_t)h->max_groups, F = (size_t)h->max_frames;
         // multi-round decoding: rounds / hand-over threshold / later-round group width (0 = defaults)
-        h->rounds = cfg->no_compaction ? 1 : (cfg->compaction_rounds > 0 ? std::min(cfg->compaction_rounds, 4) : 3);
+        h->rounds = cfg->no_compaction ? 1 : (cfg->compaction_rounds > 0 ? std::min(cfg->compaction_rounds, MAX_ROUNDS) : 3);
         h->auto_rounds = !cfg->no_compaction && cfg->compaction_rounds <= 0;
-        h->exit_eighths = cfg->compaction_exit_eighths > 0 ? std::min(cfg->compaction_exit_eighths, 6) : 4;
+        h->exit_eighths = cfg->compaction_exit_eighths > 0 ? std::min(cfg->compaction_exit_eighths, 7) : 4;
         h->nf_later = ldpc_later_frames_per_lane(cfg->precision, cfg->compaction_nf_later);
         h->ext_cap = h->rounds > 1 ? (int)region_b_offset(h, (h->max_frames + 255) / 256 * 256) + 512 : 0;
-        h->ext_slots = h->rounds > 1 ? (int)ext_slot_offset(h, (h->max_frames + 255) / 256 * 256) + 1024 : 0;
+        h->ext_slots = h->rounds > 1 ? (int)ext_slot_offset(h, (h->max_frames + 255) / 256 * 256) + 256 * MAX_ROUNDS : 0;
         const size_t FE = F + h->ext_cap;                    // var / cn slots
         const size_t FS = F + h->ext_slots, GS = FS / 32;    // hd / out_hd / bookkeeping slots
         int rc;
@@ -652,7 +675,7 @@ extern "C"
             (rc = ensure(h, h->surv_mask, GS * 4 + 4)) || (rc = ensure(h, h->surv_iters, FS * 4 + 4)) ||
             (rc = ensure(h, h->dst_base, GS * 4 + 4)) || (rc = ensure(h, h->src_of_dst, FS * 4 + 4)) ||
             (rc = ensure(h, h->slot_frame, FS * 4 + 4)) || (rc = ensure(h, h->slot_iters, FS * 4 + 4)) ||
-            (rc = ensure(h, h->final_loc, F * 4 + 4)) || (rc = ensure(h, h->n_surv, 32 * sizeof(int))) ||
+            (rc = ensure(h, h->final_loc, F * 4 + 4)) || (rc = ensure(h, h->n_surv, 64 * sizeof(int))) ||
             (rc = ensure(h, h->rem, G * BCH_NPOLY * GF_M * 4)) || (rc = ensure(h, h->nz, G * 4)) ||
             (rc = ensure(h, h->cwd_ldpc, F)) || (rc = ensure(h, h->cwd_bch, F)) || (rc = ensure(h, h->nit, F * 4)) ||
             (rc = ensure(h, h->stats, STAT_COUNT * sizeof(unsigned long long))))

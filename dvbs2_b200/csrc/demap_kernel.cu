@@ -116,6 +116,12 @@ demap_frames_kernel(const DemapLaunch a, float* __restrict__ llr, int deinterlea
 template<typename R, int NF>
 struct LaneVec;
 template<>
+struct LaneVec<float, 1>
+{
+    using T = float;
+    __device__ static T make(const float* x) { return x[0]; }
+};
+template<>
 struct LaneVec<float, 2>
 {
     using T = float2;
@@ -329,11 +335,16 @@ template<int BPS>
 static cudaError_t
 demap_to_var_bps(const DemapLaunch& a, void* var, int precision, int nf, cudaStream_t s)
 {
-    // the group width is fixed by the precision (ldpc_frames_per_lane): 2 for float, 4 for int16 and int8
-    if (nf != (precision == 0 ? 2 : 4)) return cudaErrorInvalidValue;
+    // the group width follows the precision: 1 or 2 (chosen per call) for float, 4 for int16 and int8
+    if (precision == 0 ? (nf != 1 && nf != 2) : nf != 4) return cudaErrorInvalidValue;
     switch (precision)
     {
-        case 0: demap_to_var_launch<BPS, float, 2>(a, var, s); break;
+        case 0:
+            if (nf == 1)
+                demap_to_var_launch<BPS, float, 1>(a, var, s);
+            else
+                demap_to_var_launch<BPS, float, 2>(a, var, s);
+            break;
         case 1: demap_to_var_launch<BPS, int16_t, 4>(a, var, s); break;
         case 2: demap_to_var_launch<BPS, int8_t, 4>(a, var, s); break;
         default: return cudaErrorInvalidValue;

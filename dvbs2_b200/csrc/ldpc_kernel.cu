@@ -1066,9 +1066,8 @@ launch_merge_back(const MergeLaunch& c, cudaStream_t s)
 }
 
 cudaError_t
-launch_pack_llr(const void* in, void* var, int precision, int n_frames, cudaStream_t s)
+launch_pack_llr(const void* in, void* var, int precision, int n_frames, int nf, cudaStream_t s)
 {
-    const int nf = ldpc_frames_per_lane(precision);
     const int groups = (n_frames + 32 * nf - 1) / (32 * nf);
     const dim3 grid((N_LDPC + 31) / 32, groups * nf), block(32, 8);
     switch (precision)

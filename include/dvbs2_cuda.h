@@ -82,7 +82,10 @@ extern "C"
         int compaction_exit_eighths; /* a group hands its live frames over once fewer than this many eighths of its
                                         frames still iterate, 1..6 (0 = default 4)                                   */
         int compaction_nf_later;     /* frames per lane in rounds >= 2: f32 1 or 2 (0 = 1), int16 2 or 4 (0 = 2)   */
-        int reserved[3]; /* must be 0                                                                      */
+        int ldpc_frames_per_lane;    /* f32 only: frames per lane of round 1, 1 (32-frame groups: lowest latency) or 2
+                                      * (64-frame groups, 256-byte chunks: highest throughput); 0 = chosen per call from
+                                      * the batch size (1 while the call fits in one wave of 32-frame groups)           */
+        int reserved[2]; /* must be 0                                                                      */
     } dvbs2_cuda_cfg;
 
     typedef struct

@@ -1,0 +1,29 @@
+#!/usr/bin/env bash
+cd "${GRAFT_REPO_ROOT:-.}"
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_ldpc.py -q -m gpu -x -k "compaction" 2>&1 | tail -5
+: > gpurun_out/exp_u.jsonl
+run() { echo "## $*" >> gpurun_out/exp_u.jsonl; timeout 300 python bench.py --no-e2e --no-cpu --no-int16 --steps 5 --warmup 3 "$@" >> gpurun_out/exp_u.jsonl 2>> gpurun_out/exp_u.err; }
+run --rounds 4 --exit-eighths 6 --nf-later 2
+run --rounds 5 --exit-eighths 6 --nf-later 2
+run --rounds 6 --exit-eighths 6 --nf-later 2
+run --rounds 5 --exit-eighths 7 --nf-later 2
+run --rounds 6 --exit-eighths 7 --nf-later 2
+run --rounds 6 --exit-eighths 7
+run --prec i16 --rounds 5 --exit-eighths 7
+run --prec i16 --rounds 6 --exit-eighths 7
+run --prec i16 --rounds 6 --exit-eighths 6
+run --workload 8psk89 --rounds 5 --exit-eighths 6 --nf-later 2
+python - <<'PY'
+import json
+for line in open("gpurun_out/exp_u.jsonl"):
+    if line.startswith("##"):
+        print(line.strip(), end="  ->  ")
+    else:
+        try:
+            d = json.loads(line)
+            print(d["value"], d["ms_per_step"], d["config"]["frames_per_step_per_gpu"], d["stage_ms"]["ldpc"], round(d["fer"]["mean_iterations"], 3), d["gpu_launches"])
+        except Exception as e:
+            print("bad line", line[:200])
+PY
+tail -5 gpurun_out/exp_u.err

@@ -112,18 +112,21 @@ def _oracle_chain(oracle, modcod, s, llr, prec="f32", dec=2, bits=6):
     return Vl, cl, nl, Vb, cb
 
 
+@pytest.mark.parametrize("nf", [0, 2])  # frames per lane (f32): chosen by the library (1 at this size) / the large-batch shape
 @pytest.mark.parametrize("modcod,ebn0,prec", [("QPSK-S_8/9", 4.0, "f32"), ("QPSK-S_3/5", 2.4, "f32"),
                                               ("8PSK-S_3/5", 4.0, "i16"), ("8PSK-S_3/5", 4.2, "i8"),
                                               ("8PSK-S_8/9", 7.5, "f32"), ("16APSK-S_8/9", 7.8, "f32")])
-def test_fused_chain_matches_oracle_chain(oracle, modcod, ebn0, prec):
+def test_fused_chain_matches_oracle_chain(oracle, modcod, ebn0, prec, nf):
     """The chain on the device must equal oracle-LDPC + oracle-BCH run on the *GPU's own* LLRs (decoders are judged on
     identical LLRs; the demapper has its own tolerance test above)."""
     from dvbs2_b200 import Decoder_chain_DVBS2_cuda, Handle, Modem_DVBS2_cuda
 
+    if prec != "f32" and nf:
+        pytest.skip("the integer precisions have one group shape")
     mc = MODCODS[modcod]
     F = 96
     s = synth_frames(oracle, modcod, F, ebn0, seed=17)
-    h = Handle(modcod=modcod, n_frames=F, precision=prec)
+    h = Handle(modcod=modcod, n_frames=F, precision=prec, ldpc_frames_per_lane=nf)
     llr = np.zeros((F, N_LDPC), np.float32)
     Modem_DVBS2_cuda(h, F).demodulate(s["sigma"], s["rx"], llr)
     V = np.zeros((F, mc["K_bch"]), np.int32)
@@ -149,7 +152,7 @@ def test_chain_divergent_iteration_counts(oracle):
     rng = np.random.default_rng(1)
     for f in (3, 40, 77):
         s["rx"][f] += rng.standard_normal(s["rx"][f].shape).astype(np.float32) * 0.05
-    h = Handle(modcod=modcod, n_frames=F)
+    h = Handle(modcod=modcod, n_frames=F, ldpc_frames_per_lane=2)
     llr = np.zeros((F, N_LDPC), np.float32)
     Modem_DVBS2_cuda(h, F).demodulate(s["sigma"], s["rx"], llr)
     V = np.zeros((F, mc["K_bch"]), np.int32)

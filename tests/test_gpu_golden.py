@@ -35,10 +35,11 @@ def _ldpc(modcod, Y, prec, **kw):
 @pytest.mark.parametrize("modcod", ALL)
 def test_ldpc_all_precisions_vs_reference_outputs(modcod):
     g, N = load(modcod), MODCODS[modcod]["N_bch"]
-    V, cwd = _ldpc(modcod, g["llr_nat"], "f32")
-    assert np.array_equal(cwd, g["ldpc_seq_f32_cwd"]) and np.array_equal(V, ub(g["ldpc_seq_f32_V"], N))
-    ok = g["ldpc_inter_f32_cwd"] == 1  # float NMS of --dec-simd INTER: identical on every frame that converges
-    assert np.array_equal(V[ok], ub(g["ldpc_inter_f32_V"], N)[ok])
+    for nf in (1, 2):  # 32- and 64-frame groups
+        V, cwd = _ldpc(modcod, g["llr_nat"], "f32", ldpc_frames_per_lane=nf)
+        assert np.array_equal(cwd, g["ldpc_seq_f32_cwd"]) and np.array_equal(V, ub(g["ldpc_seq_f32_V"], N))
+        ok = g["ldpc_inter_f32_cwd"] == 1  # float NMS of --dec-simd INTER: identical on every frame that converges
+        assert np.array_equal(V[ok], ub(g["ldpc_inter_f32_V"], N)[ok])
     V, cwd = _ldpc(modcod, g["q16"], "i16")
     assert np.array_equal(cwd, g["ldpc_seq_i16_cwd"]) and np.array_equal(V, ub(g["ldpc_seq_i16_V"], N))
     ok = g["ldpc_inter_i16_cwd"] == 1
