@@ -287,6 +287,14 @@ class Estimator_DVBS2_cuda(_Module):
             None if Es_N0 is None else _np_ptr(Es_N0, np.float32, F, "Es_N0"), F))
 
 
+    def estimate_dev(self, X_N, SIG, Eb_N0=None, Es_N0=None):
+        F, h = self.n_frames, self.h
+        h.check(h.lib.dvbs2_cuda_estimate_dev(
+            h._h, _dev_ptr(X_N, "float32", F * self.N, "X_N"), _dev_ptr(SIG, "float32", F, "SIG"),
+            None if Eb_N0 is None else _dev_ptr(Eb_N0, "float32", F, "Eb_N0"),
+            None if Es_N0 is None else _dev_ptr(Es_N0, "float32", F, "Es_N0"), F))
+
+
 class Receiver_chain_DVBS2_cuda(_Module):
     """Fused receiver stage from PL frames: remove_plh -> estimate (or caller's sigma) -> demodulate -> deinterleave -> LDPC ->
     BCH -> optional BB descramble; int32 or bit-packed output (SURVEY §8f N1 + N2)."""

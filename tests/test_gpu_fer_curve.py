@@ -2,8 +2,8 @@
 --dec-ite 10 --dec-simd INTER --ter-freq 0 -e 100`, i.e. norm 1.0, 100 frame errors per point).  The decoders are bit-exact on
 identical LLRs (the other GPU suites); this checks the whole Monte-Carlo loop on the device — TX, Philox AWGN, chain, BB
 descrambler, BFER monitor — lands inside the joint binomial confidence interval of the reference's points.  QPSK with min-sum
-(norm 1) is invariant to the LLR scale, so the reference's estimated sigma versus the true sigma used here does not matter; the
-16APSK point was taken with the perfect estimator."""
+(norm 1) is invariant to the LLR scale, so the reference's estimated sigma versus the true sigma does not matter there; the 8PSK
+points use the on-device Estimator_DVBS2 like the reference run; the 16APSK point was taken with the perfect estimator."""
 import math
 
 import pytest
@@ -12,21 +12,23 @@ from oracle.oracle import MODCODS, N_LDPC, ebn0_to_sigma
 
 pytestmark = pytest.mark.gpu
 
-# (modcod, Eb/N0 dB, reference FER, frames to run here)
-ANCHORS = [("QPSK-S_8/9", 3.9, 0.129, 8192), ("QPSK-S_8/9", 4.0, 1.52e-2, 49152), ("QPSK-S_3/5", 2.2, 0.59, 4096),
-           ("QPSK-S_3/5", 2.5, 2.75e-3, 131072), ("16APSK-S_8/9", 7.6, 8.4e-2, 16384)]
+# (modcod, Eb/N0 dB, reference FER, frames to run here, sigma from the on-device Estimator_DVBS2 as in the reference run)
+ANCHORS = [("QPSK-S_8/9", 3.9, 0.129, 8192, False), ("QPSK-S_8/9", 4.0, 1.52e-2, 49152, True), ("QPSK-S_3/5", 2.2, 0.59, 4096, False),
+           ("QPSK-S_3/5", 2.5, 2.75e-3, 131072, False), ("8PSK-S_3/5", 3.8, 0.14, 8192, True),
+           ("8PSK-S_3/5", 4.0, 1.36e-3, 131072, True), ("8PSK-S_8/9", 6.6, 0.22, 4096, True),
+           ("16APSK-S_8/9", 7.6, 8.4e-2, 16384, False)]
 
 
-@pytest.mark.parametrize("modcod,ebn0,ref_fer,frames", ANCHORS)
-def test_fer_inside_the_reference_confidence_interval(modcod, ebn0, ref_fer, frames):
+@pytest.mark.parametrize("modcod,ebn0,ref_fer,frames,estimate", ANCHORS)
+def test_fer_inside_the_reference_confidence_interval(modcod, ebn0, ref_fer, frames, estimate):
     import torch
 
-    from dvbs2_b200 import Decoder_chain_DVBS2_cuda, Handle, Transmitter_DVBS2_cuda
+    from dvbs2_b200 import Decoder_chain_DVBS2_cuda, Estimator_DVBS2_cuda, Handle, Transmitter_DVBS2_cuda
 
     mc = MODCODS[modcod]
     F = 16384 if frames >= 16384 else frames
     h = Handle(modcod=modcod, n_ite=10, n_frames=F)
-    tx, ch = Transmitter_DVBS2_cuda(h, F), Decoder_chain_DVBS2_cuda(h, F)
+    tx, ch, est = Transmitter_DVBS2_cuda(h, F), Decoder_chain_DVBS2_cuda(h, F), Estimator_DVBS2_cuda(h, F)
     dev = torch.device("cuda:0")
     cp = torch.zeros(F, dtype=torch.float32, device=dev)
     sym = torch.zeros((F, 2 * N_LDPC // mc["bps"]), dtype=torch.float32, device=dev)
@@ -36,6 +38,8 @@ def test_fer_inside_the_reference_confidence_interval(modcod, ebn0, ref_fer, fra
     for b in range(frames // F):
         tx.random_payload(1000 + b)
         tx.modulate_awgn_dev(sigma, 77 + b, cp, sym)
+        if estimate:  # the 8PSK points of the reference were taken with --est-type DVBS2 (its default): sigma from M2/M4
+            est.estimate_dev(sym, cp)
         ch.demodulate_decode_dev(cp, sym, c1, c2, V, None)
         tx.check_errors()
     mon = tx.monitor()
