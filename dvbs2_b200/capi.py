@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdvbs2_cuda.so")
+LIB_PATH = os.environ.get("DVBS2_CUDA_LIB") or os.path.join(HERE, "libdvbs2_cuda.so")  # override: kernel-variant experiments
 
 N_LDPC = 16200
 OK, ERR_INVALID, ERR_CUDA, ERR_TOO_MANY, ERR_NOMEM = 0, -1, -2, -3, -4

@@ -168,8 +168,6 @@ __device__ __forceinline__ uint32_t signmask(uint32_t x)
 __device__ __forceinline__ uint32_t bitmask(uint32_t w, int b) { return signmask(w << (15 - b)); }
 // per half: m ? a : b
 __device__ __forceinline__ uint32_t mux(uint32_t a, uint32_t b, uint32_t m) { return (a & m) | (b & ~m); }
-// 0xffff in every half of x that is zero
-__device__ __forceinline__ uint32_t zeromask(uint32_t x) { return signmask(__vadd2(x, 0xffffffffu) & ~x & 0x80008000u); }
 __device__ __forceinline__ int lo(uint32_t x) { return (int)(short)(x & 0xffffu); }
 __device__ __forceinline__ int hi(uint32_t x) { return (int)(short)(x >> 16); }
 __device__ __forceinline__ uint32_t pair(int l, int h) { return ((uint32_t)l & 0xffffu) | ((uint32_t)h << 16); }
