@@ -259,3 +259,40 @@ def test_errors_are_reported_not_swallowed():
     with pytest.raises(ValueError):
         dec.set_n_frames(h.info["max_frames"] + 1)
     h.close()
+
+
+def test_empty_batches_and_bad_arguments_through_the_c_abi():
+    """Zero frames is a no-op that touches no buffer; too many frames, NULL buffers and ambiguous outputs are refused with the
+    documented status codes (no exception crosses the ABI, nothing is silently clamped)."""
+    import ctypes as C
+
+    from dvbs2_b200 import Handle, capi
+
+    h = Handle(modcod="QPSK-S_8/9", n_frames=64)
+    L, K = h.lib, h.info["K_bch"]
+    cp = np.full(64, 0.3, np.float32)
+    sym = np.zeros((64, 16200), np.float32)
+    V = np.full((64, K), 7, np.int32)
+    cw = np.full(64, 7, np.int8)
+    P = np.full((64, K // 8), 7, np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    launches = h.stats()["kernel_launches"]
+    assert L.dvbs2_cuda_chain(h._h, p(cp), p(sym), p(cw), p(cw), p(V), None, 0) == capi.OK
+    assert L.dvbs2_cuda_chain_packed(h._h, p(cp), p(sym), None, None, p(P), None, 1, 0) == capi.OK
+    assert L.dvbs2_cuda_ldpc_decode_siho(h._h, p(sym), p(cw), p(V), None, 0) == capi.OK
+    assert L.dvbs2_cuda_bch_decode_hiho(h._h, p(V), p(cw), p(V), 0) == capi.OK
+    assert L.dvbs2_cuda_demodulate(h._h, p(cp), p(sym), p(sym), 0) == capi.OK
+    assert L.dvbs2_cuda_rx_chain(h._h, p(sym), None, None, None, None, p(V), None, 1, None, 0) == capi.OK
+    assert (V == 7).all() and (cw == 7).all() and (P == 7).all() and h.stats()["kernel_launches"] == launches
+    too_many = h.info["max_frames"] + 1
+    assert L.dvbs2_cuda_chain(h._h, p(cp), p(sym), None, None, p(V), None, too_many) == capi.ERR_TOO_MANY
+    assert L.dvbs2_cuda_chain(h._h, p(cp), p(sym), None, None, p(V), None, -1) == capi.ERR_INVALID
+    assert L.dvbs2_cuda_chain(h._h, None, p(sym), None, None, p(V), None, 64) == capi.ERR_INVALID
+    assert L.dvbs2_cuda_chain(h._h, p(cp), p(sym), None, None, None, None, 64) == capi.ERR_INVALID
+    assert L.dvbs2_cuda_chain_packed(h._h, p(cp), p(sym), None, None, None, None, 0, 64) == capi.ERR_INVALID
+    # rx_chain wants exactly one output format
+    pl = np.zeros((64, h.lib.dvbs2_cuda_pl_frame_size(h._h)), np.float32)
+    assert L.dvbs2_cuda_rx_chain(h._h, p(pl), None, None, None, None, p(V), p(P), 1, None, 64) == capi.ERR_INVALID
+    assert L.dvbs2_cuda_rx_chain(h._h, p(pl), None, None, None, None, None, None, 1, None, 64) == capi.ERR_INVALID
+    assert (V == 7).all()
+    h.close()
