@@ -59,6 +59,7 @@ struct dvbs2_cuda_handle
     int nf = 1, n_sms = 148;             // frames per lane of the LDPC kernel (group = 32 * nf frames)
     int k8 = 0;
     size_t elt = 4; // sizeof(R)
+    int coop_max = 32768; // float calls of up to this many frames use the cooperative small-batch LDPC kernel (0 = never)
     int nf_cfg = 0; // float only: frames per lane forced by the configuration (0 = chosen per call from the batch size)
     int cn_div = 1; // check state: 16 / cn_div bytes per frame and check (int16 packs two frames into one uint4)
     cudaStream_t stream = nullptr;
@@ -203,6 +204,15 @@ call_nf(const dvbs2_cuda_handle* h, int n_frames)
     return n_frames <= h->n_sms * LDPC_WARPS * 32 ? 1 : 2;
 }
 
+// Small float calls go to the cooperative kernel (a CTA per 32-frame group, ldpc_kernel.cu): below ~32k frames a call is bound
+// by the length of its dependency chain, which that kernel shortens by an order of magnitude; above, the multi-round
+// lane = frame kernel moves fewer bytes per frame (frame compaction) in larger chunks.
+bool
+call_coop(const dvbs2_cuda_handle* h, int n_frames, int nf)
+{
+    return h->cfg.precision == DVBS2_PREC_F32 && nf == 1 && h->coop_max > 0 && n_frames <= h->coop_max;
+}
+
 // `first_frame` is a multiple of the group size 32 * nf; per-frame offsets follow from the layouts in kernels.h
 LdpcLaunch
 ldpc_args(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frames, int8_t* cwd, int32_t* n_iter, int nf)
@@ -283,6 +293,12 @@ int
 run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frames, int8_t* d_cwd, int32_t* d_nit, int nf0)
 {
     LdpcLaunch a = ldpc_args(h, s, first_frame, n_frames, d_cwd, d_nit, nf0);
+    if (call_coop(h, n_frames, nf0))
+    {
+        CU(h, launch_ldpc_decode_coop(a, s));
+        h->launches += 1;
+        return DVBS2_OK;
+    }
     const bool multi = h->rounds > 1 && h->ext_cap > 0 && h->cfg.early_stop && h->cfg.n_ite >= 4 && a.n_groups >= 2;
     if (!multi)
     {
@@ -592,6 +608,7 @@ extern "C"
         h->k8 = k8;
         h->elt = cfg->precision == DVBS2_PREC_F32 ? 4 : cfg->precision == DVBS2_PREC_I16 ? 2 : 1;
         h->nf = ldpc_frames_per_lane(cfg->precision);
+        h->coop_max = cfg->ldpc_coop_max_frames < 0 ? 0 : cfg->ldpc_coop_max_frames > 0 ? cfg->ldpc_coop_max_frames : 32768;
         h->nf_cfg = cfg->ldpc_frames_per_lane; // float only (validated above): 1 or 2 in round 1; 0 = per call from the batch size
         h->cn_div = cfg->precision == DVBS2_PREC_I16 ? 2 : 1;
         h->max_frames = (cfg->max_frames + 32 * h->nf - 1) / (32 * h->nf) * (32 * h->nf);

@@ -85,7 +85,10 @@ extern "C"
         int ldpc_frames_per_lane;    /* f32 only: frames per lane of round 1, 1 (32-frame groups: lowest latency) or 2
                                       * (64-frame groups, 256-byte chunks: highest throughput); 0 = chosen per call from
                                       * the batch size (1 while the call fits in one wave of 32-frame groups)           */
-        int reserved[2]; /* must be 0                                                                      */
+        int ldpc_coop_max_frames;    /* f32 only: calls of up to this many frames (with one frame per lane) use the
+                                      * cooperative small-batch LDPC kernel — a CTA per 32-frame group, ~10x shorter calls
+                                      * below a few thousand frames, one round, same results; 0 = default 32768, < 0 = never */
+        int reserved[1]; /* must be 0                                                                      */
     } dvbs2_cuda_cfg;
 
     typedef struct

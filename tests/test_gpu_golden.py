@@ -35,8 +35,8 @@ def _ldpc(modcod, Y, prec, **kw):
 @pytest.mark.parametrize("modcod", ALL)
 def test_ldpc_all_precisions_vs_reference_outputs(modcod):
     g, N = load(modcod), MODCODS[modcod]["N_bch"]
-    for nf in (1, 2):  # 32- and 64-frame groups
-        V, cwd = _ldpc(modcod, g["llr_nat"], "f32", ldpc_frames_per_lane=nf)
+    for nf, coop in ((1, 0), (1, -1), (2, 0)):  # cooperative small-batch kernel, 32- and 64-frame groups of the lane = frame kernel
+        V, cwd = _ldpc(modcod, g["llr_nat"], "f32", ldpc_frames_per_lane=nf, ldpc_coop_max_frames=coop)
         assert np.array_equal(cwd, g["ldpc_seq_f32_cwd"]) and np.array_equal(V, ub(g["ldpc_seq_f32_V"], N))
         ok = g["ldpc_inter_f32_cwd"] == 1  # float NMS of --dec-simd INTER: identical on every frame that converges
         assert np.array_equal(V[ok], ub(g["ldpc_inter_f32_V"], N)[ok])

@@ -19,13 +19,15 @@ def _llrs(oracle, modcod, F, ebn0, seed=1):
 
 
 def _decode(modcod, Y, prec="f32", n_ite=10, norm=1.0, early_stop=True, compaction=True, **cfg):
-    """Float calls run twice unless the caller pins it: with 32-frame groups (what the library picks for small batches) and
-    with 64-frame groups (the large-batch shape); both must give the same bits, CWD and iteration counts."""
+    """Float calls run three times unless the caller pins it: through the cooperative small-batch kernel (what the library
+    picks at these sizes), through the lane = frame kernel with 32-frame groups, and with 64-frame groups (the large-batch
+    shape); all must give the same bits, CWD and iteration counts."""
     if prec == "f32" and "ldpc_frames_per_lane" not in cfg:
         a = _decode(modcod, Y, prec, n_ite, norm, early_stop, compaction, ldpc_frames_per_lane=1, **cfg)
-        b = _decode(modcod, Y, prec, n_ite, norm, early_stop, compaction, ldpc_frames_per_lane=2, **cfg)
-        assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3]))
-        return b
+        b = _decode(modcod, Y, prec, n_ite, norm, early_stop, compaction, ldpc_frames_per_lane=1, ldpc_coop_max_frames=-1, **cfg)
+        c = _decode(modcod, Y, prec, n_ite, norm, early_stop, compaction, ldpc_frames_per_lane=2, **cfg)
+        assert all(np.array_equal(x, y) for x, y in zip(a[:3], c[:3])) and all(np.array_equal(x, y) for x, y in zip(b[:3], c[:3]))
+        return c
     from dvbs2_b200 import Decoder_LDPC_DVBS2_cuda, Handle
 
     F = Y.shape[0]
