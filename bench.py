@@ -57,7 +57,7 @@ def parse():
     p.add_argument("--rounds", type=int, default=0, help="decoding rounds (frame compaction between rounds); 0 = library default")
     p.add_argument("--exit-eighths", type=int, default=0, help="hand-over threshold in eighths of a group; 0 = library default")
     p.add_argument("--nf-later", type=int, default=0, help="f32: frames per lane in rounds >= 2; 0 = library default")
-    p.add_argument("--coop-max", type=int, default=0, help="f32: largest call that uses the cooperative small-batch LDPC kernel (0 = library default 32768, -1 = never)")
+    p.add_argument("--coop-max", type=int, default=0, help="f32: largest call that uses the cooperative small-batch LDPC kernel (0 = library default 16384, -1 = never)")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--cpu-threads", type=int, default=0)
     return p.parse_args()

@@ -59,7 +59,7 @@ struct dvbs2_cuda_handle
     int nf = 1, n_sms = 148;             // frames per lane of the LDPC kernel (group = 32 * nf frames)
     int k8 = 0;
     size_t elt = 4; // sizeof(R)
-    int coop_max = 32768; // float calls of up to this many frames use the cooperative small-batch LDPC kernel (0 = never)
+    int coop_max = 16384; // float calls of up to this many frames use the cooperative small-batch LDPC kernel (0 = never)
     int nf_cfg = 0; // float only: frames per lane forced by the configuration (0 = chosen per call from the batch size)
     int cn_div = 1; // check state: 16 / cn_div bytes per frame and check (int16 packs two frames into one uint4)
     cudaStream_t stream = nullptr;
@@ -608,7 +608,7 @@ extern "C"
         h->k8 = k8;
         h->elt = cfg->precision == DVBS2_PREC_F32 ? 4 : cfg->precision == DVBS2_PREC_I16 ? 2 : 1;
         h->nf = ldpc_frames_per_lane(cfg->precision);
-        h->coop_max = cfg->ldpc_coop_max_frames < 0 ? 0 : cfg->ldpc_coop_max_frames > 0 ? cfg->ldpc_coop_max_frames : 32768;
+        h->coop_max = cfg->ldpc_coop_max_frames < 0 ? 0 : cfg->ldpc_coop_max_frames > 0 ? cfg->ldpc_coop_max_frames : 16384;
         h->nf_cfg = cfg->ldpc_frames_per_lane; // float only (validated above): 1 or 2 in round 1; 0 = per call from the batch size
         h->cn_div = cfg->precision == DVBS2_PREC_I16 ? 2 : 1;
         h->max_frames = (cfg->max_frames + 32 * h->nf - 1) / (32 * h->nf) * (32 * h->nf);

@@ -87,7 +87,7 @@ extern "C"
                                       * the batch size (1 while the call fits in one wave of 32-frame groups)           */
         int ldpc_coop_max_frames;    /* f32 only: calls of up to this many frames (with one frame per lane) use the
                                       * cooperative small-batch LDPC kernel — a CTA per 32-frame group, ~10x shorter calls
-                                      * below a few thousand frames, one round, same results; 0 = default 32768, < 0 = never */
+                                      * below a few thousand frames, one round, same results; 0 = default 16384, < 0 = never */
         int reserved[1]; /* must be 0                                                                      */
     } dvbs2_cuda_cfg;
 
