@@ -684,21 +684,23 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
 }
 
 // ---------------------------------------------------------------------------------------------- small batches
-// Cooperative variant for small batches (float, one frame per lane): the COOP_WARPS warps of a CTA decode ONE 32-frame group
-// together, warp w taking checks w, w + W, w + 2W, ...  Everything a check does except its incoming parity-chain edge is
-// independent of the chain (the information variables of checks closer than min_reuse_distance are disjoint, and var[K+c]
-// still holds last iteration's value), so a warp turns its check's loads into t and partial minima ahead of time, then waits
-// for var[K+c-1] from the warp that owns check c-1 (shared-memory slot + mbarrier), folds that one edge in, hands
-// var[K+c] on at once, and only then computes and stores the other new messages.  The dependent part per check is ~100 cycles
-// instead of a whole check (~2400 cycles: HBM latency + 900 instructions), which is what bounds a call when there are too few
-// groups to fill the machine: 1024 frames take 2-3 ms instead of 22 ms.  Same arithmetic, same order of the operations that
-// do not commute (min / max / XOR are exact and order-free), so results are bit-identical to the kernel above.
-// One round only (no frame compaction): a group occupies a CTA for at most n_ite iterations.
-constexpr int COOP_WARPS = 16;
+// Cooperative variant for small batches (float, one frame per lane): a CTA decodes ONE 32-frame group.  Everything a check does
+// except its incoming parity-chain edge is independent of the chain (the information variables of checks closer than
+// min_reuse_distance are disjoint, and var[K+c] still holds last iteration's value).  So the work is split by role:
+//   * COOP_WORKERS worker warps: worker u takes checks u, u + 15, ...; it loads its check 15 checks ahead, turns the loads into
+//     t = var - msg for every edge but the chain edge, reduces them to (min1, min2, sign parity) and posts those, the outgoing
+//     parity edge's t and the chain edge's old message in its shared-memory slot; when the chain warp has answered, it computes
+//     and stores the new messages of all its edges (pass 2) and the compressed check state.
+//   * ONE chain warp walks the checks in natural order with var[K+c-1] in a register: per check it reads the five posted words,
+//     folds the chain edge in, forms the two output magnitudes and var[K+c], and posts (t_chain, min1, c1, c2, sign parity)
+//     back — about ten dependent instructions per check instead of a whole check (~2400 cycles: HBM latency + 900 instructions),
+//     which is what bounds a call when there are too few groups to fill the machine.
+// Slots are guarded by mbarriers (one "posted", one "answered" per worker), so waiting warps are suspended by the hardware
+// rather than spinning.  Same arithmetic, same order of the operations that do not commute (min / max / XOR are exact and
+// order-free), so results are bit-identical to the kernel above.  One round only (no frame compaction).
+constexpr int COOP_WORKERS = 15;
+constexpr int COOP_WARPS = COOP_WORKERS + 1;
 
-// One mbarrier per hand-over slot (one producer warp, one consumer warp, expected arrival count 1): waiting warps are
-// suspended by the hardware instead of spinning — fifteen spinning warps starved the one warp on the critical path of its
-// issue slots (measured: 10 ms instead of 2 ms per group).
 __device__ __forceinline__ void
 mbar_init(uint64_t* bar, unsigned count)
 {
@@ -726,35 +728,33 @@ template<int DI>
 __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(const LdpcLaunch a)
 {
     using A = Arith<float>;
-    constexpr int W = COOP_WARPS;
+    constexpr int NWK = COOP_WORKERS;
     constexpr int D = DI + 2;        // edges per check incl. the two parity edges (bit DI = in, DI+1 = out)
     constexpr int IW = (DI + 1) / 2; // u32 words per index row
     constexpr unsigned VB = 32 * sizeof(float);
+    constexpr int SLOT = 10 * 32;    // words per worker slot: 5 posted + 5 answered, 32 lanes each
 
     extern __shared__ uint32_t smem[];
     const int K = a.K, M = a.M;
     uint32_t* s_idx = smem;                   // [M][IW]
     uint32_t* s_last = smem + (size_t)M * IW; // [M]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + (((size_t)M * IW + M + 1) & ~(size_t)1)); // [W] one per slot
-    float* s_chain = reinterpret_cast<float*>(s_bar + W); // [W][32] var[K+c] after check c, slot c % W
-    unsigned* s_unsat = reinterpret_cast<unsigned*>(s_chain + W * 32); // [1] OR of the unsatisfied-check masks of all warps
+    uint64_t* s_posted = reinterpret_cast<uint64_t*>(smem + (((size_t)M * IW + M + 1) & ~(size_t)1)); // [NWK]
+    uint64_t* s_answered = s_posted + NWK;                                                              // [NWK]
+    uint32_t* s_slot = reinterpret_cast<uint32_t*>(s_answered + NWK);                                   // [NWK][SLOT]
+    unsigned* s_unsat = s_slot + NWK * SLOT; // [1] OR of the unsatisfied-check masks of all warps
     int* s_group = reinterpret_cast<int*>(s_unsat + 1);
     for (int i = threadIdx.x; i < M * IW; i += blockDim.x)
         s_idx[i] = a.idx32[i];
     for (int i = threadIdx.x; i < M; i += blockDim.x)
         s_last[i] = a.last[i];
-    if (threadIdx.x < W) mbar_init(s_bar + threadIdx.x, 1);
+    if (threadIdx.x < 2 * NWK) mbar_init(s_posted + threadIdx.x, 1);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool chain_warp = w == NWK; // the last warp walks the chain, warps 0 .. NWK-1 are workers
     const int n_groups = (a.n_frames + 31) / 32;
-    // warp w always consumes slot (w - 1) % W (checks c = w mod W read var[K+c-1] of check c-1 = w-1 mod W) and is its only
-    // consumer; the k-th wait matches the producer's k-th arrival, so the phase parity is the warp's own wait count
-    uint64_t* const bar_in = s_bar + (w + W - 1) % W;
-    uint64_t* const bar_out = s_bar + w;
-    const float* const chain_in = s_chain + ((w + W - 1) % W) * 32 + lane;
-    float* const chain_out = s_chain + w * 32 + lane;
-    unsigned n_waits = 0;
+    unsigned n_turns = 0;   // worker: checks posted so far (phase parity of its two barriers)
+    unsigned visits = 0;    // chain warp, lane u: checks of worker u answered so far
 
     for (;;)
     {
@@ -778,118 +778,137 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
         {
             const bool mine = (active >> lane) & 1;
             const bool have_state = ite > 0;
-            float v[DI + 1]; // information variables of the check, then var[K+c]
-            uint4 st;
-            auto issue = [&](int c) {
-                const uint32_t* row = s_idx + c * IW;
-#pragma unroll
-                for (int i = 0; i < DI; i++)
-                {
-                    const unsigned vi = (row[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-                    v[i] = __ldcg(reinterpret_cast<const float*>(vbytes + (vi * VB + loff)));
-                }
-                v[DI] = __ldcg(reinterpret_cast<const float*>(vbytes + ((unsigned)(K + c) * VB + loff)));
-                st = have_state ? __ldcg(cn + (size_t)c * 32) : make_uint4(0u, 0u, 0u, 0u);
-            };
-            if (w < M) issue(w);
-#pragma unroll 1
-            for (int c = w; c < M; c += W)
+            if (chain_warp)
             {
-                const uint32_t* row = s_idx + c * IW;
-                const uint32_t lastm = s_last[c];
-                // ---- everything but the incoming chain edge (pass 1 of Update_rule_MS.hxx:57-67 on D - 1 edges)
-                const float o1 = __uint_as_float(st.x), o2 = __uint_as_float(st.y);
-                const unsigned osg = st.z, oeq = st.w;
-                float t[D];
-                unsigned sa = 0;
-                float m1 = FLT_MAX, m2 = FLT_MAX;
-#pragma unroll
-                for (int i = 0; i < D; i++)
+                // ---- the chain: x = var[K+c-1] after check c-1, per lane (= frame)
+                float x = FLT_MAX;
+#pragma unroll 1
+                for (int c = 0; c < M; c++)
                 {
-                    if (i == DI) continue;
-                    const int b = D - 1 - i;
-                    const float mag = (oeq & (1u << b)) ? o1 : o2;
-                    const float ti = A::sub(v[i < DI ? i : DI], A::apply_sign(mag, osg << (31 - b)));
-                    t[i] = ti;
+                    const int u = c % NWK;
+                    uint32_t* sl = s_slot + u * SLOT + lane;
+                    const unsigned par = __shfl_sync(FULL, visits, u) & 1u;
+                    if (lane == u) visits++;
+                    mbar_wait_acquire(s_posted + u, par);
+                    float m1 = __uint_as_float(sl[0 * 32]), m2 = __uint_as_float(sl[1 * 32]);
+                    unsigned sa = sl[2 * 32];
+                    const float t_out = __uint_as_float(sl[3 * 32]);
+                    const float msg_in = __uint_as_float(sl[4 * 32]);
+                    const float ti = c == 0 ? FLT_MAX : A::sub(x, msg_in); // check 0 has no incoming chain edge
                     const float ab = fabsf(ti);
                     sa ^= __float_as_uint(ti);
                     m2 = fminf(m2, fmaxf(ab, m1));
                     m1 = fminf(m1, ab);
+                    const float c1 = fmaxf(0.f, A::normalize(m2, a.norm, a.k8)); // Update_rule_NMS.hxx:100-106
+                    const float c2 = fmaxf(0.f, A::normalize(m1, a.norm, a.k8));
+                    const bool e = fabsf(t_out) == m1;
+                    x = A::add(t_out, A::apply_sign(e ? c1 : c2, sa ^ __float_as_uint(t_out))); // var[K+c]
+                    sl[5 * 32] = __float_as_uint(ti);
+                    sl[6 * 32] = __float_as_uint(m1);
+                    sl[7 * 32] = __float_as_uint(c1);
+                    sl[8 * 32] = __float_as_uint(c2);
+                    sl[9 * 32] = sa;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_release(s_answered + u);
                 }
-                const float mag_in = (oeq & 2u) ? o1 : o2; // the chain edge is edge DI: bit D - 1 - DI = 1
-                const unsigned sgn_in = osg << 30;
-                if (c + W < M) issue(c + W);
-
-                // ---- the chain edge: var[K+c-1] as check c-1 left it
-                float ti;
-                if (c == 0)
-                    ti = FLT_MAX; // check 0 has no incoming chain edge
-                else
-                {
-                    mbar_wait_acquire(bar_in, n_waits & 1u);
-                    n_waits++;
-                    ti = A::sub(*chain_in, A::apply_sign(mag_in, sgn_in));
-                }
-                t[DI] = ti;
-                {
-                    const float ab = fabsf(ti);
-                    sa ^= __float_as_uint(ti);
-                    m2 = fminf(m2, fmaxf(ab, m1));
-                    m1 = fminf(m1, ab);
-                }
-                const float c1 = fmaxf(0.f, A::normalize(m2, a.norm, a.k8)); // Update_rule_NMS.hxx:100-106
-                const float c2 = fmaxf(0.f, A::normalize(m1, a.norm, a.k8));
-
-                // ---- new messages (Update_rule_MS.hxx:82-92, ...layered.hxx:198-203): the outgoing chain edge first
-                unsigned nsg = 0, neq = 0;
-                float nv[D];
+            }
+            else
+            {
+                float v[DI + 1]; // information variables of the check, then var[K+c]
+                uint4 st;
+                auto issue = [&](int c) {
+                    const uint32_t* row = s_idx + c * IW;
 #pragma unroll
-                for (int k = 0; k < D; k++)
-                {
-                    const int i = (k == 0) ? DI + 1 : k - 1; // order: D-1 (chain out), 0, 1, ..., DI
-                    const float tt = t[i];
-                    const bool e = fabsf(tt) == m1;
-                    const unsigned x = sa ^ __float_as_uint(tt); // bit 31: sign of the new message
-                    nv[i] = A::add(tt, A::apply_sign(e ? c1 : c2, x));
-                    if (e) neq |= 1u << (D - 1 - i);
-                    nsg |= (x >> 31) << (D - 1 - i);
-                    if (k == 0 && c != M - 1)
-                    { // hand var[K+c] to the owner of check c+1
-                        *chain_out = nv[i];
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_release(bar_out);
+                    for (int i = 0; i < DI; i++)
+                    {
+                        const unsigned vi = (row[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+                        v[i] = __ldcg(reinterpret_cast<const float*>(vbytes + (vi * VB + loff)));
                     }
-                }
+                    v[DI] = __ldcg(reinterpret_cast<const float*>(vbytes + ((unsigned)(K + c) * VB + loff)));
+                    st = have_state ? __ldcg(cn + (size_t)c * 32) : make_uint4(0u, 0u, 0u, 0u);
+                };
+                uint32_t* sl = s_slot + w * SLOT + lane;
+                if (w < M) issue(w);
+#pragma unroll 1
+                for (int c = w; c < M; c += NWK)
+                {
+                    const uint32_t* row = s_idx + c * IW;
+                    const uint32_t lastm = s_last[c];
+                    // ---- every edge but the incoming chain edge (pass 1 of Update_rule_MS.hxx:57-67 on D - 1 edges)
+                    const float o1 = __uint_as_float(st.x), o2 = __uint_as_float(st.y);
+                    const unsigned osg = st.z, oeq = st.w;
+                    float t[D];
+                    unsigned sa = 0;
+                    float m1 = FLT_MAX, m2 = FLT_MAX;
 #pragma unroll
-                for (int i = 0; i < D; i++)
-                {
-                    unsigned vi;
-                    bool ballot;
-                    if (i < DI)
+                    for (int i = 0; i < D; i++)
                     {
-                        vi = (row[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-                        ballot = (lastm >> i) & 1u;
+                        if (i == DI) continue;
+                        const int b = D - 1 - i;
+                        const float mag = (oeq & (1u << b)) ? o1 : o2;
+                        const float ti = A::sub(v[i < DI ? i : DI], A::apply_sign(mag, osg << (31 - b)));
+                        t[i] = ti;
+                        const float ab = fabsf(ti);
+                        sa ^= __float_as_uint(ti);
+                        m2 = fminf(m2, fmaxf(ab, m1));
+                        m1 = fminf(m1, ab);
                     }
-                    else if (i == DI)
+                    // the chain edge is edge DI: bit D - 1 - DI = 1 of the state words
+                    sl[0 * 32] = __float_as_uint(m1);
+                    sl[1 * 32] = __float_as_uint(m2);
+                    sl[2 * 32] = sa;
+                    sl[3 * 32] = __float_as_uint(t[DI + 1]);
+                    sl[4 * 32] = __float_as_uint(A::apply_sign((oeq & 2u) ? o1 : o2, osg << 30));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_release(s_posted + w);
+                    if (c + NWK < M) issue(c + NWK);
+
+                    mbar_wait_acquire(s_answered + w, n_turns & 1u);
+                    n_turns++;
+                    t[DI] = __uint_as_float(sl[5 * 32]);
+                    m1 = __uint_as_float(sl[6 * 32]);
+                    const float c1 = __uint_as_float(sl[7 * 32]), c2 = __uint_as_float(sl[8 * 32]);
+                    sa = sl[9 * 32];
+
+                    // ---- new messages (Update_rule_MS.hxx:82-92, ...layered.hxx:198-203)
+                    unsigned nsg = 0, neq = 0;
+#pragma unroll
+                    for (int i = 0; i < D; i++)
                     {
-                        if (c == 0) continue;
-                        vi = K + c - 1;
-                        ballot = true; // check c is the last one to touch parity variable K+c-1
+                        const float tt = t[i];
+                        const bool e = fabsf(tt) == m1;
+                        const unsigned xs = sa ^ __float_as_uint(tt); // bit 31: sign of the new message
+                        const float nv = A::add(tt, A::apply_sign(e ? c1 : c2, xs));
+                        if (e) neq |= 1u << (D - 1 - i);
+                        nsg |= (xs >> 31) << (D - 1 - i);
+                        unsigned vi;
+                        bool ballot;
+                        if (i < DI)
+                        {
+                            vi = (row[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+                            ballot = (lastm >> i) & 1u;
+                        }
+                        else if (i == DI)
+                        {
+                            if (c == 0) continue;
+                            vi = K + c - 1;
+                            ballot = true; // check c is the last one to touch parity variable K+c-1
+                        }
+                        else
+                        {
+                            if (c != M - 1) continue; // stored by check c+1 (as its incoming edge); only the last check stores it
+                            vi = K + c;
+                            ballot = true;
+                        }
+                        if (mine) __stcg(reinterpret_cast<float*>(vbytes + (vi * VB + loff)), nv);
+                        if (ballot)
+                        {
+                            const unsigned hw = __ballot_sync(FULL, nv < 0.f);
+                            if (lane == 0) __stcg(hd + vi, hw);
+                        }
                     }
-                    else
-                    {
-                        if (c != M - 1) continue; // stored by check c+1 (as its incoming edge); only the last check stores it
-                        vi = K + c;
-                        ballot = true;
-                    }
-                    if (mine) __stcg(reinterpret_cast<float*>(vbytes + (vi * VB + loff)), nv[i]);
-                    if (ballot)
-                    {
-                        const unsigned hw = __ballot_sync(FULL, nv[i] < 0.f);
-                        if (lane == 0) __stcg(hd + vi, hw);
-                    }
+                    if (mine) __stcg(cn + (size_t)c * 32, make_uint4(__float_as_uint(c1), __float_as_uint(c2), nsg, neq));
                 }
-                if (mine) __stcg(cn + (size_t)c * 32, make_uint4(__float_as_uint(c1), __float_as_uint(c2), nsg, neq));
             }
             my_iters += mine ? 1 : 0;
             if (threadIdx.x == 0) *s_unsat = 0;
@@ -1270,7 +1289,7 @@ static cudaError_t
 launch_ldpc_coop_k(const LdpcLaunch& a, cudaStream_t s)
 {
     auto k = ldpc_decode_coop_kernel<DI>;
-    const size_t smem = ((size_t)a.M * ((DI + 1) / 2) + a.M + 1 + 2 * COOP_WARPS + COOP_WARPS * 32 + 2) * sizeof(uint32_t);
+    const size_t smem = ((size_t)a.M * ((DI + 1) / 2) + a.M + 1 + 4 * COOP_WORKERS + COOP_WORKERS * 320 + 2) * sizeof(uint32_t);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(a.queue, 0, sizeof(int), s);
