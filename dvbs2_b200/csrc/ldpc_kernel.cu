@@ -780,20 +780,32 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
             const bool have_state = ite > 0;
             if (chain_warp)
             {
-                // ---- the chain: x = var[K+c-1] after check c-1, per lane (= frame)
+                // ---- the chain: x = var[K+c-1] after check c-1, per lane (= frame).  The words posted for check c+1 are
+                //      fetched before check c is computed: they do not depend on the chain, and their shared-memory latency
+                //      (and the barrier test) then lie beside the dependent instructions instead of between them.
                 float x = FLT_MAX;
-#pragma unroll 1
-                for (int c = 0; c < M; c++)
-                {
+                float n_m1, n_m2, n_tout, n_msg;
+                unsigned n_sa;
+                auto fetch = [&](int c) {
                     const int u = c % NWK;
-                    uint32_t* sl = s_slot + u * SLOT + lane;
+                    const uint32_t* sl = s_slot + u * SLOT + lane;
                     const unsigned par = __shfl_sync(FULL, visits, u) & 1u;
                     if (lane == u) visits++;
                     mbar_wait_acquire(s_posted + u, par);
-                    float m1 = __uint_as_float(sl[0 * 32]), m2 = __uint_as_float(sl[1 * 32]);
-                    unsigned sa = sl[2 * 32];
-                    const float t_out = __uint_as_float(sl[3 * 32]);
-                    const float msg_in = __uint_as_float(sl[4 * 32]);
+                    n_m1 = __uint_as_float(sl[0 * 32]), n_m2 = __uint_as_float(sl[1 * 32]);
+                    n_sa = sl[2 * 32];
+                    n_tout = __uint_as_float(sl[3 * 32]);
+                    n_msg = __uint_as_float(sl[4 * 32]);
+                };
+                fetch(0);
+#pragma unroll 1
+                for (int c = 0; c < M; c++)
+                {
+                    uint32_t* sl = s_slot + (c % NWK) * SLOT + lane;
+                    float m1 = n_m1, m2 = n_m2;
+                    unsigned sa = n_sa;
+                    const float t_out = n_tout, msg_in = n_msg;
+                    if (c + 1 < M) fetch(c + 1);
                     const float ti = c == 0 ? FLT_MAX : A::sub(x, msg_in); // check 0 has no incoming chain edge
                     const float ab = fabsf(ti);
                     sa ^= __float_as_uint(ti);
@@ -809,7 +821,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
                     sl[8 * 32] = __float_as_uint(c2);
                     sl[9 * 32] = sa;
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_release(s_answered + u);
+                    if (lane == 0) mbar_arrive_release(s_answered + (c % NWK));
                 }
             }
             else

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_ldpc.py tests/test_gpu_golden.py -q -m gpu -x 2>&1 | tail -4
+timeout -k 10 400 python -m pytest tests/test_gpu_ldpc.py tests/test_gpu_golden.py -q -m gpu -x 2>&1 | tail -4
 : > gpurun_out/exp_coop3.jsonl
 run() { echo "## $*" >> gpurun_out/exp_coop3.jsonl; timeout 300 python bench.py --no-cpu --no-int16 --no-e2e --steps 8 --warmup 3 "$@" >> gpurun_out/exp_coop3.jsonl 2>> gpurun_out/exp_coop3.err; }
 run --frames 1024
