@@ -75,6 +75,7 @@ struct dvbs2_cuda_handle
     float* d_cstl = nullptr;
     uint8_t* d_scr_bytes = nullptr; // BB scrambler sequence, 8 bits per byte, LSB first
     BchDevTables bch{};
+    BchLaunch bch_seg{}; // seg_len / seg_mul of the segmented syndrome division (per MODCOD)
     // decoder state
     DevBuf var, cn, hd, out_hd, rem, nz, cwd_ldpc, cwd_bch, nit, stats;
     // frame compaction (multi-round decoding).  var/cn: region A = slots [0, max_frames) (rounds 1, 3), region B =
@@ -252,6 +253,8 @@ bch_args(dvbs2_cuda_handle* h, int first_frame, int n_frames, int8_t* cwd)
     b.stats = (unsigned long long*)h->stats.p;
     b.n_frames = n_frames, b.n_groups = (n_frames + 31) / 32;
     b.N = h->mc.N_bch, b.K = h->mc.K_bch;
+    b.seg_len = h->bch_seg.seg_len;
+    memcpy(b.seg_mul, h->bch_seg.seg_mul, sizeof(b.seg_mul));
     return b;
 }
 
@@ -673,6 +676,8 @@ extern "C"
         }
         h->bch.alpha_to = h->d_alpha_to, h->bch.index_of = h->d_index_of;
         memcpy(h->bch.minpoly, bt.minpoly, sizeof(bt.minpoly));
+        h->bch_seg.N = mc.N_bch;
+        bch_segment_table(h->bch_seg, bt.minpoly);
         memcpy(h->bch.poly_of, bt.poly_of, sizeof(bt.poly_of));
         memcpy(h->bch.synd_mat, bt.synd_mat, sizeof(bt.synd_mat));
 

@@ -158,7 +158,12 @@ struct BchLaunch
     unsigned long long* stats;
     int n_frames, n_groups;
     int N, K;         // shortened BCH length and payload
+    // segmented division: lane j of a warp divides bits [j * seg_len, (j + 1) * seg_len) and scales its remainder by
+    // seg_mul[p][j] = x^(number of bits after the segment) mod m_p(x), low 14 coefficients (filled by bch_segment_table)
+    int seg_len;
+    uint16_t seg_mul[BCH_NPOLY][32];
 };
+void bch_segment_table(BchLaunch& a, const uint16_t* minpoly_low14); // host: seg_len / seg_mul from N
 cudaError_t launch_bch_decode(const BchLaunch& a, const BchDevTables& t, cudaStream_t s);
 
 // on-device transmitter / channel / monitor (tx_kernel.cu); all buffers bit-sliced per group of 32 frames
