@@ -17,6 +17,14 @@
  *   dvbs2_cuda_chain             <- the four tasks above bound back to back as in D/mains/TX_RX_BB/main.cpp:87-91
  *                                   (pipeline stage 6 of D/mains/RX/main_8-sta.cpp:291-296), fused on the device
  *   dvbs2_cuda_quantize          <- Quantizer_pow2::_process, A/src/Module/Quantizer/Pow2/Quantizer_pow2.cpp:184-190
+ *   dvbs2_cuda_remove_plh        <- Framer<B>::remove_plh, D/common/Module/Framer/Framer.hxx:319-343
+ *   dvbs2_cuda_estimate          <- Estimator<R>::estimate codelet, D/common/Module/Estimator/Estimator.hxx:103-117
+ *                                   (-> Estimator_DVBS2::_estimate, D/common/Module/Estimator/Estimator_DVBS2.hxx:31-58)
+ *   dvbs2_cuda_rx_chain          <- remove_plh, estimate, the four decode tasks and Scrambler_BB::descramble
+ *                                   (D/common/Module/Scrambler/Scrambler_BB/Scrambler_BB.hxx:51-72) as bound in
+ *                                   D/mains/TX_RX_BB/main.cpp:86-92, fused on the device
+ *   dvbs2_cuda_chain_packed      <- dvbs2_cuda_chain with the payload packed like spu::tools::Bit_packer::pack
+ *                                   (S/include/Tools/Algo/Bit_packer/Bit_packer.hxx, LSB first), optional descramble
  *
  * Conventions (same as the reference sockets): buffers are frame-major and contiguous,
  * LLR/symbols/sigma are float, bits are int32_t (0/1), CWD is int8_t (1 = decoder holds a valid codeword).
@@ -78,9 +86,9 @@ extern "C"
         int no_compaction; /* 0 (default): frames still iterating when most of their group has converged are packed
                               into dense groups for the remaining iterations (same results, fewer bytes moved);
                               1: every frame stays in its group                                                  */
-        int compaction_rounds;       /* decoding rounds incl. the first, 2..4 (0 = default 2)                       */
+        int compaction_rounds;       /* decoding rounds incl. the first, 2..6 (0 = 2, or 3 from two waves of groups on) */
         int compaction_exit_eighths; /* a group hands its live frames over once fewer than this many eighths of its
-                                        frames still iterate, 1..6 (0 = default 4)                                   */
+                                        frames still iterate, 1..7 (0 = default 4)                                   */
         int compaction_nf_later;     /* frames per lane in rounds >= 2: f32 1 or 2 (0 = 1), int16 2 or 4 (0 = 2)   */
         int ldpc_frames_per_lane;    /* f32 only: frames per lane of round 1, 1 (32-frame groups: lowest latency) or 2
                                       * (64-frame groups, 256-byte chunks: highest throughput); 0 = chosen per call from
