@@ -209,8 +209,14 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    real_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its banner ("NCCL version ...") with printf on the process's stdout when the image sets NCCL_DEBUG; the
+        # contract is ONE JSON line there, so fd 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -471,7 +477,10 @@ def main():
                     "monitor": {"frames": int(mon[0]), "bit_errors": int(mon[1]), "frame_errors": int(mon[2]),
                                 "fer": mon[2] / max(1, mon[0]), "ber": mon[1] / max(1, mon[0] * K_bch)}},
         }
-        print(json.dumps(out))
+        sys.stdout.flush()
+        if real_stdout is not None:
+            os.dup2(real_stdout, 1)
+        print(json.dumps(out), flush=True)
     if h is not None:
         h.close()
     if world > 1:
