@@ -62,7 +62,14 @@ def test_argument_validation_needs_no_gpu():
     c2 = capi.Cfg.from_buffer_copy(cfg)
     c2.precision, c2.norm = capi.PREC["i16"], 0.3  # integer decoders only know k/8 (Update_rule_NMS.hxx:14-39)
     assert lib.dvbs2_cuda_create(C.byref(c2), C.byref(h)) == capi.ERR_INVALID
+    c2 = capi.Cfg.from_buffer_copy(cfg)
+    c2.ldpc_frames_per_lane = 3  # the float kernel knows 32- and 64-frame groups only
+    assert lib.dvbs2_cuda_create(C.byref(c2), C.byref(h)) == capi.ERR_INVALID
+    c2 = capi.Cfg.from_buffer_copy(cfg)
+    c2.precision, c2.ldpc_frames_per_lane = capi.PREC["i16"], 1  # the integer precisions have one group shape
+    assert lib.dvbs2_cuda_create(C.byref(c2), C.byref(h)) == capi.ERR_INVALID
     assert lib.dvbs2_cuda_sync(None) == capi.ERR_INVALID and lib.dvbs2_cuda_destroy(None) == capi.OK
+    assert lib.dvbs2_cuda_pl_frame_size(None) == capi.ERR_INVALID
 
 
 def test_no_cpu_fallback_without_a_device():
