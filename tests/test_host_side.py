@@ -169,3 +169,29 @@ def test_counter_reduction_world_size_2_gloo():
     for rank, tot, done, rates, t in res:
         assert tot == want and done and t == 1.5
         assert abs(rates["fer"] - want["n_fe"] / 1001) < 1e-12 and abs(rates["ber"] - want["n_be"] / 10010) < 1e-12
+
+
+def test_committed_bench_line_follows_the_driver_contract():
+    """The bench line recorded from the final code of the round (profiles/r1_bench_v10.json) carries every key the driver and
+    the judge read, with consistent values."""
+    import json
+
+    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_v10.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["unit"] == "Mbit/s" and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["dtype"] == "f32" and "workload" in d["config"] and d["gpu_launches"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-4 and r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] == "reference" and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["matches_device_path"] is True
+    assert e["value"] < d["value"]  # host buffers over PCIe cannot beat the device-resident rate
+    K_bch = 14232
+    frames = d["config"]["frames_per_step_per_gpu"] * d["steps"] * d["n_gpus"]
+    assert abs(d["value"] - K_bch * frames / (d["ms_per_step"] * d["steps"] * 1e-3) / 1e6) / d["value"] < 1e-3
+    ref = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_v10_reference_arm.json")))
+    assert ref["impl"] == "reference" and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] == "reference"
