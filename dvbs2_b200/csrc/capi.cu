@@ -64,7 +64,6 @@ struct dvbs2_cuda_handle
     int cn_div = 1; // check state: 16 / cn_div bytes per frame and check (int16 packs two frames into one uint4)
     cudaStream_t stream = nullptr;
     cudaStream_t pipe[N_PIPE] = {};
-    cudaEvent_t pipe_done[N_PIPE] = {};
     // code tables
     uint16_t* d_idx = nullptr;
     uint32_t* d_idx32 = nullptr;
@@ -88,7 +87,7 @@ struct dvbs2_cuda_handle
     int exit_eighths = 4; // a group hands its live frames over once fewer than exit_eighths/8 of its frames still iterate
     int nf_later = 1;     // frames per lane in rounds >= 2
     // staging for the host-buffer entry points (grown on demand, never beyond max_frames)
-    DevBuf in_a, in_b, out_a, sigma;
+    DevBuf in_a, out_a, sigma;
     // transmitter / monitor (allocated on first use)
     DevBuf tx_src, tx_cw, tx_scr, tx_gmask, mon;
     bool tx_encoded = false;
@@ -561,7 +560,7 @@ extern "C"
         for (DevBuf* b : { &h->var, &h->cn, &h->hd, &h->out_hd, &h->rem, &h->nz, &h->cwd_ldpc, &h->cwd_bch, &h->nit,
                            &h->stats, &h->surv_mask, &h->surv_iters, &h->dst_base, &h->src_of_dst, &h->slot_frame, &h->slot_iters,
                            &h->final_loc, &h->n_surv,
-                           &h->in_a, &h->in_b, &h->out_a, &h->sigma, &h->tx_src, &h->tx_cw, &h->tx_scr,
+                           &h->in_a, &h->out_a, &h->sigma, &h->tx_src, &h->tx_cw, &h->tx_scr,
                            &h->tx_gmask, &h->mon })
             if (b->p) cudaFree(b->p);
         for (void* p : { (void*)h->d_idx, (void*)h->d_idx32, (void*)h->d_last, (void*)h->d_queue, (void*)h->d_alpha_to,
@@ -570,7 +569,6 @@ extern "C"
         for (int i = 0; i < N_PIPE; i++)
         {
             if (h->pipe[i]) cudaStreamDestroy(h->pipe[i]);
-            if (h->pipe_done[i]) cudaEventDestroy(h->pipe_done[i]);
         }
         if (h->stream) cudaStreamDestroy(h->stream);
         for (auto& m : h->marks)
@@ -648,7 +646,6 @@ extern "C"
         for (int i = 0; i < N_PIPE; i++)
         {
             CUB(cudaStreamCreateWithFlags(&h->pipe[i], cudaStreamNonBlocking));
-            CUB(cudaEventCreateWithFlags(&h->pipe_done[i], cudaEventDisableTiming));
         }
         CUB(cudaMalloc(&h->d_idx, h->lt.idx.size() * sizeof(uint16_t)));
         CUB(cudaMemcpy(h->d_idx, h->lt.idx.data(), h->lt.idx.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
