@@ -90,7 +90,7 @@ struct dvbs2_cuda_handle
     DevBuf in_a, out_a, sigma;
     // transmitter / monitor (allocated on first use)
     DevBuf tx_src, tx_cw, tx_scr, tx_gmask, mon;
-    bool tx_encoded = false;
+    int tx_encoded_groups = 0; // 32-frame groups of the current payload that launch_tx_encode has encoded
     uint64_t launches = 0;
     std::string last_error;
     // profiling
@@ -655,8 +655,11 @@ extern "C"
         CUB(cudaMemcpy(h->d_last, h->lt.last.data(), h->lt.last.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         CUB(cudaMalloc(&h->d_queue, 64 * sizeof(int)));
         CUB(cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, cfg->device));
-        // the decoder prefetches one check ahead: legal only while no two checks that close share an information variable
+        // the lane = frame decoder prefetches one check ahead: legal only while no two checks that close share an information
+        // variable; the cooperative kernel's worker pipeline runs 3 * COOP_WORKERS checks deep (ldpc_kernel.cu) and is
+        // switched off for a table that is denser than that
         if (h->lt.min_reuse_distance < 4) return bail(DVBS2_ERR_INVALID);
+        if (h->lt.min_reuse_distance < ldpc_coop_min_reuse()) h->coop_max = 0;
         CUB(cudaMalloc(&h->d_alpha_to, bt.alpha_to.size() * sizeof(uint16_t)));
         CUB(cudaMemcpy(h->d_alpha_to, bt.alpha_to.data(), bt.alpha_to.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
         CUB(cudaMalloc(&h->d_index_of, bt.index_of.size() * sizeof(int16_t)));
@@ -1112,7 +1115,7 @@ extern "C"
         CU(h, cudaMemcpyAsync(h->in_a.p, U, bytes, cudaMemcpyHostToDevice, s));
         CU(h, launch_pack_bits((const int32_t*)h->in_a.p, (uint32_t*)h->tx_src.p, h->mc.K_bch, h->mc.K_bch, n_frames, s));
         h->launches += 1;
-        h->tx_encoded = false;
+        h->tx_encoded_groups = 0;
         CU(h, cudaStreamSynchronize(s));
         return DVBS2_OK;
     }
@@ -1125,7 +1128,7 @@ extern "C"
         TRY(tx_init(h));
         CU(h, launch_tx_random_payload((uint32_t*)h->tx_src.p, h->mc.K_bch, (n_frames + 31) / 32, seed, h->stream));
         h->launches += 1;
-        h->tx_encoded = false;
+        h->tx_encoded_groups = 0;
         return DVBS2_OK;
     }
 
@@ -1137,11 +1140,11 @@ extern "C"
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
         const TxLaunch t = tx_args(h, n_frames);
-        if (!h->tx_encoded)
-        {
+        if (h->tx_encoded_groups < t.n_groups)
+        { // a later call may ask for more frames of the same payload than the one that triggered the encoder
             CU(h, launch_tx_encode(t, h->stream));
             h->launches += 2;
-            h->tx_encoded = true;
+            h->tx_encoded_groups = t.n_groups;
         }
         CU(h, launch_tx_modulate_awgn(t, h->d_cstl, d_Y_N1, d_CP, h->mc.bps, h->mc.n_sym, h->mc.itl_cols, h->mc.itl_rev,
                                       sigma, seed, h->stream));
@@ -1155,11 +1158,11 @@ extern "C"
         if (!out || stage < 0 || stage > 3 || !h->tx_src.p) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
-        if (stage > 0 && !h->tx_encoded)
+        if (stage > 0 && h->tx_encoded_groups < (n_frames + 31) / 32)
         {
             CU(h, launch_tx_encode(tx_args(h, n_frames), h->stream));
             h->launches += 2;
-            h->tx_encoded = true;
+            h->tx_encoded_groups = (n_frames + 31) / 32;
         }
         const int len = stage <= 1 ? h->mc.K_bch : stage == 2 ? h->mc.N_bch : N_LDPC;
         const uint32_t* words = stage == 0 ? (const uint32_t*)h->tx_src.p : (const uint32_t*)h->tx_cw.p;

@@ -95,6 +95,8 @@ int ldpc_frames_per_lane(int precision); // NF: 2 (f32, i16), 4 (i8)
 cudaError_t launch_ldpc_decode(const LdpcLaunch& a, int precision, cudaStream_t s);
 // float, 32-frame groups, a whole CTA per group (small batches): same results, one round
 cudaError_t launch_ldpc_decode_coop(const LdpcLaunch& a, cudaStream_t s);
+// smallest distance (in checks) between two checks sharing an information variable that the cooperative kernel tolerates
+int ldpc_coop_min_reuse();
 cudaError_t launch_pack_llr(const void* in, void* var, int precision, int n_frames, int nf, cudaStream_t s);
 // scr (optional): BB scrambler sequence, 8 bits per byte LSB first, XORed into the output (Scrambler_BB::descramble)
 cudaError_t launch_unpack_bits(const uint32_t* words, int32_t* out, int stride, int K, int n_frames, cudaStream_t s,

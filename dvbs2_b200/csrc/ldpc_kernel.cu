@@ -666,7 +666,8 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
             if (fin)
             {
                 const int frame = a.slot_frame ? a.slot_frame[slot] : slot;
-                const bool ok = !((failed[j] >> lane) & 1);
+                // without the syndrome test the reference reports every frame as valid (Decoder_LDPC_BP.hxx:8-20: status 0, CWD 1)
+                const bool ok = !a.early_stop || !((failed[j] >> lane) & 1);
                 if (a.cwd) a.cwd[frame] = (int8_t)ok;
                 if (a.n_iter) a.n_iter[frame] = my_iters[j];
             }
@@ -700,6 +701,12 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
 // order-free), so results are bit-identical to the kernel above.  One round only (no frame compaction).
 constexpr int COOP_WORKERS = 15;
 constexpr int COOP_WARPS = COOP_WORKERS + 1;
+// Hazard bound of the worker pipeline: a worker requests the variables of check c + COOP_WORKERS right after posting check c,
+// while the answers (and hence the stores) of checks c - 2 * COOP_WORKERS + 1 .. c + COOP_WORKERS - 1 may still be outstanding
+// (its own previous check has stored; every other worker can be one full turn behind).  So no two checks closer than
+// 3 * COOP_WORKERS may share an information variable.  The DVB-S2 short-frame tables give 55 (rate 8/9) and 52 (rate 3/5);
+// dvbs2_cuda_create turns the cooperative kernel off for a table that does not satisfy this (ldpc_coop_min_reuse()).
+constexpr int COOP_MIN_REUSE = 3 * COOP_WORKERS;
 
 __device__ __forceinline__ void
 mbar_init(uint64_t* bar, unsigned count)
@@ -965,7 +972,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
             const bool fin = (done >> lane) & 1;
             if (fin)
             {
-                const bool ok = !((failed >> lane) & 1);
+                const bool ok = !a.early_stop || !((failed >> lane) & 1);
                 if (a.cwd) a.cwd[slot] = (int8_t)ok;
                 if (a.n_iter) a.n_iter[slot] = my_iters;
             }
@@ -1309,6 +1316,12 @@ launch_ldpc_coop_k(const LdpcLaunch& a, cudaStream_t s)
     const int groups = (a.n_frames + 31) / 32;
     k<<<groups < a.n_sms ? groups : a.n_sms, COOP_WARPS * 32, smem, s>>>(a);
     return cudaGetLastError();
+}
+
+int
+ldpc_coop_min_reuse()
+{
+    return COOP_MIN_REUSE;
 }
 
 // float, one frame per lane, one round: the cooperative small-batch kernel

@@ -198,7 +198,9 @@ norm_eighths(float f)
             }                                                                                                          \
             for (int i = 0; i < H->K; i++)                                                                             \
                 V_K[(size_t)f * H->K + i] = !(var[i] >= 0);                                                            \
-            cwd[f] = (int8_t)ok;                                                                                       \
+            /* enable_syndrome == false: check_syndrome_soft is never consulted, _decode returns 0 and CWD = 1             \
+             * (Decoder_LDPC_BP.hxx:8-20, ...horizontal_layered.hxx:120-123) */                                            \
+            cwd[f] = (int8_t)(early_stop ? ok : 1);                                                                    \
             if (n_iter_out) n_iter_out[f] = ite;                                                                       \
             if (var_out) memcpy(var_out + (size_t)f * N_LDPC, var, sizeof(R) * N_LDPC);                                \
         }                                                                                                              \

@@ -95,6 +95,17 @@ class Oracle:
         assert rc == 0, rc
         return (V, cwd, nit, var) if want_var else (V, cwd, nit)
 
+    def ldpc_decode_mt(self, K, Y, threads, **kw):
+        """ldpc_decode over `threads` Python threads (ctypes releases the GIL): for the >= 1e4-frame parity runs."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        Y = np.asarray(Y).reshape(-1, N_LDPC)
+        self.H(K)  # build the table once, before the threads race for it
+        cuts = np.linspace(0, Y.shape[0], max(1, min(threads, Y.shape[0])) + 1).astype(int)
+        with ThreadPoolExecutor(len(cuts) - 1) as ex:
+            parts = list(ex.map(lambda i: self.ldpc_decode(K, Y[cuts[i]:cuts[i + 1]], **kw), range(len(cuts) - 1)))
+        return tuple(np.concatenate([p[j] for p in parts]) for j in range(3))
+
     def ldpc_encode(self, K, U):
         U = _c(U, np.int32).reshape(-1, K)
         X = np.zeros((U.shape[0], N_LDPC), np.int32)
@@ -240,8 +251,11 @@ class Ref:
         L.ref_bch_new.argtypes = [C.c_int, C.c_int]
         L.ref_bch_free.argtypes = [C.c_void_p]
         L.ref_bch_decode.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        for f in ("ref_ldpc_seq_f32", "ref_ldpc_seq_i16", "ref_ldpc_seq_i8", "ref_ldpc_inter_f32", "ref_ldpc_inter_i16"):
+        for f in ("ref_ldpc_seq_f32", "ref_ldpc_seq_i16", "ref_ldpc_seq_i8", "ref_ldpc_inter_f32", "ref_ldpc_inter_i16",
+                  "ref_ldpc_tinter_f32", "ref_ldpc_tinter_i16", "ref_ldpc_seq_f32_nosyn"):
             getattr(L, f).argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_ldpc_mt.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int] + [C.c_void_p] * 3
+        L.ref_bch_decode_mt.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 3
         L.ref_tx.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int] + [C.c_void_p] * 6
         L.ref_demodulate.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_int] + [C.c_void_p] * 5
         L.ref_bench_chain.restype = C.c_double
@@ -264,15 +278,26 @@ class Ref:
         self.lib.ref_build_H(K, C.byref(M), C.byref(E), _p(deg), _p(cols))
         return deg, cols
 
-    def ldpc_decode(self, K, Y, n_ite=10, norm=1.0, prec="f32", simd=False):
+    def ldpc_decode(self, K, Y, n_ite=10, norm=1.0, prec="f32", simd=False, threads=1, enable_syndrome=True):
+        """simd: False = sequential decoder (row a7), True = ONMS_inter (a8, what --dec-simd INTER builds),
+        "tinter" = the templated ..._inter<Update_rule_NMS_simd> of C++17 builds (a9).  threads > 1 splits the frames
+        over that many decoder instances."""
         dt = {"f32": np.float32, "i16": np.int16, "i8": np.int8}[prec]
         bt = {"f32": np.int32, "i16": np.int16, "i8": np.int8}[prec]
         Y = _c(Y, dt).reshape(-1, N_LDPC)
         F = Y.shape[0]
         cwd = np.zeros(F, np.int8)
         V = np.zeros((F, K), bt)
-        fn = getattr(self.lib, "ref_ldpc_%s_%s" % ("inter" if simd else "seq", prec))
-        rc = fn(K, n_ite, norm, F, _p(Y), _p(cwd), _p(V))
+        kind = {False: "seq", True: "inter", "tinter": "tinter"}[simd]
+        if not enable_syndrome:
+            assert kind == "seq" and prec == "f32" and threads == 1
+            rc = self.lib.ref_ldpc_seq_f32_nosyn(K, n_ite, norm, F, _p(Y), _p(cwd), _p(V))
+        elif threads > 1:
+            assert prec in ("f32", "i16")
+            rc = self.lib.ref_ldpc_mt({"seq": 0, "inter": 1, "tinter": 2}[kind], 0 if prec == "f32" else 1, K, n_ite, norm, F,
+                                      threads, _p(Y), _p(cwd), _p(V))
+        else:
+            rc = getattr(self.lib, "ref_ldpc_%s_%s" % (kind, prec))(K, n_ite, norm, F, _p(Y), _p(cwd), _p(V))
         assert rc >= 0, rc
         return V.astype(np.int32), cwd
 
@@ -284,13 +309,16 @@ class Ref:
         self.lib.ref_bch_tables(_p(a), _p(i), _p(g), C.byref(n))
         return a, i, g[: n.value]
 
-    def bch_decode(self, K, N, Y):
-        if (K, N) not in self._bch:
-            self._bch[(K, N)] = self.lib.ref_bch_new(K, N)
+    def bch_decode(self, K, N, Y, threads=1):
         Y = _c(Y, np.int32).reshape(-1, N)
         F = Y.shape[0]
         cwd = np.zeros(F, np.int8)
         V = np.zeros((F, K), np.int32)
+        if threads > 1:
+            assert self.lib.ref_bch_decode_mt(K, N, F, threads, _p(Y), _p(cwd), _p(V)) == 0
+            return V, cwd
+        if (K, N) not in self._bch:
+            self._bch[(K, N)] = self.lib.ref_bch_new(K, N)
         self.lib.ref_bch_decode(self._bch[(K, N)], F, _p(Y), _p(cwd), _p(V))
         return V, cwd
 

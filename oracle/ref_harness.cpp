@@ -25,6 +25,8 @@
 
 #include "Module/Decoder/LDPC/BP/Horizontal_layered/Decoder_LDPC_BP_horizontal_layered.hpp"
 #include "Module/Decoder/LDPC/BP/Horizontal_layered/ONMS/Decoder_LDPC_BP_horizontal_layered_ONMS_inter.hpp"
+#include "Module/Decoder/LDPC/BP/Horizontal_layered/Decoder_LDPC_BP_horizontal_layered_inter.hpp" // C++17 only
+#include "Tools/Code/LDPC/Update_rule/NMS/Update_rule_NMS_simd.hpp"
 #include "Tools/Code/LDPC/Update_rule/NMS/Update_rule_NMS.hpp"
 #include "Tools/Code/LDPC/Standard/DVBS2/DVBS2_constants.hpp"
 
@@ -51,14 +53,15 @@ info_pos(int K)
 
 template<typename B, typename R>
 int
-ldpc_seq(int K, int n_ite, float norm, int n_frames, const R* Y, int8_t* cwd, B* V)
+ldpc_seq(int K, int n_ite, float norm, int n_frames, const R* Y, int8_t* cwd, B* V, bool enable_syndrome = true)
 {
     const int N = 16200;
     auto dv = tools::build_dvbs2(K, N);
     auto H = tools::build_H(*dv);
     auto ibp = info_pos(K);
     tools::Update_rule_NMS<R> rule(norm);
-    module::Decoder_LDPC_BP_horizontal_layered<B, R, tools::Update_rule_NMS<R>> dec(K, N, n_ite, H, ibp, rule, true, 1);
+    module::Decoder_LDPC_BP_horizontal_layered<B, R, tools::Update_rule_NMS<R>> dec(K, N, n_ite, H, ibp, rule,
+                                                                                   enable_syndrome, 1);
     dec.set_n_frames(1);
     for (int f = 0; f < n_frames; f++)
         dec.decode_siho(Y + (size_t)f * N, cwd + f, V + (size_t)f * K);
@@ -80,6 +83,58 @@ ldpc_inter(int K, int n_ite, float norm, int n_frames, const R* Y, int8_t* cwd, 
     for (int f = 0; f < n_frames; f += W)
         dec.decode_siho(Y + (size_t)f * N, cwd + f, V + (size_t)f * K);
     return W;
+}
+
+// the templated inter-frame SIMD decoder AFF3CT's factory builds in C++17 builds
+// (Decoder_LDPC.cpp:540-650: Update_rule_NMS_simd<Q> for float, <Q, k8> with norm = k8/8 for the integer types)
+template<typename B, typename R, class Rule>
+int
+ldpc_tinter_rule(int K, int n_ite, float norm, int n_frames, const R* Y, int8_t* cwd, B* V)
+{
+    const int N = 16200;
+    auto dv = tools::build_dvbs2(K, N);
+    auto H = tools::build_H(*dv);
+    auto ibp = info_pos(K);
+    module::Decoder_LDPC_BP_horizontal_layered_inter<B, R, Rule> dec(K, N, n_ite, H, ibp, Rule(norm), true, 1);
+    const int W = (int)mipp::N<R>();
+    if (n_frames % W) return -1;
+    dec.set_n_frames(W);
+    for (int f = 0; f < n_frames; f += W)
+        dec.decode_siho(Y + (size_t)f * N, cwd + f, V + (size_t)f * K);
+    return W;
+}
+template<typename B, typename R>
+int
+ldpc_tinter(int K, int n_ite, float norm, int n_frames, const R* Y, int8_t* cwd, B* V)
+{
+    if (sizeof(R) == 4) return ldpc_tinter_rule<B, R, tools::Update_rule_NMS_simd<R>>(K, n_ite, norm, n_frames, Y, cwd, V);
+#define K8(k)                                                                                                          \
+    if (norm == 0.125f * k) return ldpc_tinter_rule<B, R, tools::Update_rule_NMS_simd<R, k>>(K, n_ite, norm, n_frames, Y, cwd, V)
+    K8(1); K8(2); K8(3); K8(4); K8(5); K8(6); K8(7); K8(8);
+#undef K8
+    return -2;
+}
+
+// frames [0, n_frames) split over n_threads decoder instances (whole SIMD waves per thread)
+template<typename F>
+int
+run_mt(int n_frames, int n_threads, int wave, F&& body)
+{
+    if (n_threads < 1) n_threads = 1;
+    const int waves = (n_frames + wave - 1) / wave;
+    n_threads = std::min(n_threads, std::max(1, waves));
+    std::vector<std::thread> th;
+    std::vector<int> rc(n_threads, 0);
+    for (int t = 0; t < n_threads; t++)
+    {
+        const int f0 = (int)((long)waves * t / n_threads) * wave;
+        const int f1 = std::min(n_frames, (int)((long)waves * (t + 1) / n_threads) * wave);
+        th.emplace_back([&, t, f0, f1]() { rc[t] = f1 > f0 ? body(f0, f1 - f0) : 0; });
+    }
+    for (auto& x : th) x.join();
+    int worst = 0;
+    for (int r : rc) worst = std::min(worst, r);
+    return worst;
 }
 } // namespace
 
@@ -128,6 +183,46 @@ extern "C"
         return ldpc_inter<int16_t, int16_t>(K, n_ite, norm, n_frames, Y, cwd, V);
     }
 
+    // a9: Decoder_LDPC_BP_horizontal_layered_inter<B,R,Update_rule_NMS_simd<R[,k8]>> (…_inter.hxx:95-108,220-271)
+    int ref_ldpc_tinter_f32(int K, int n_ite, float norm, int n_frames, const float* Y, int8_t* cwd, int32_t* V)
+    {
+        return ldpc_tinter<int32_t, float>(K, n_ite, norm, n_frames, Y, cwd, V);
+    }
+    int ref_ldpc_tinter_i16(int K, int n_ite, float norm, int n_frames, const int16_t* Y, int8_t* cwd, int16_t* V)
+    {
+        return ldpc_tinter<int16_t, int16_t>(K, n_ite, norm, n_frames, Y, cwd, V);
+    }
+    // enable_syndrome = false (Decoder_LDPC_BP.hxx:8-20: the syndrome is never tested, status 0, CWD = 1)
+    int ref_ldpc_seq_f32_nosyn(int K, int n_ite, float norm, int n_frames, const float* Y, int8_t* cwd, int32_t* V)
+    {
+        return ldpc_seq<int32_t, float>(K, n_ite, norm, n_frames, Y, cwd, V, false);
+    }
+
+    // the same decoders, frames split over n_threads instances (for >= 1e4-frame parity runs on the GPU box's host cores).
+    // kind: 0 sequential, 1 ONMS_inter, 2 templated inter;  prec: 0 float/int32 bits, 1 int16
+    int ref_ldpc_mt(int kind, int prec, int K, int n_ite, float norm, int n_frames, int n_threads, const void* Y, int8_t* cwd,
+                    void* V)
+    {
+        const size_t N = 16200;
+        const int wave = kind == 0 ? 1 : (prec == 0 ? (int)mipp::N<float>() : (int)mipp::N<int16_t>());
+        if (kind != 0 && n_frames % wave) return -1;
+        return run_mt(n_frames, n_threads, wave, [&](int f0, int n) {
+            if (prec == 0)
+            {
+                const float* y = (const float*)Y + (size_t)f0 * N;
+                int32_t* v = (int32_t*)V + (size_t)f0 * K;
+                return kind == 0   ? ldpc_seq<int32_t, float>(K, n_ite, norm, n, y, cwd + f0, v)
+                       : kind == 1 ? ldpc_inter<int32_t, float>(K, n_ite, norm, n, y, cwd + f0, v)
+                                   : ldpc_tinter<int32_t, float>(K, n_ite, norm, n, y, cwd + f0, v);
+            }
+            const int16_t* y = (const int16_t*)Y + (size_t)f0 * N;
+            int16_t* v = (int16_t*)V + (size_t)f0 * K;
+            return kind == 0   ? ldpc_seq<int16_t, int16_t>(K, n_ite, norm, n, y, cwd + f0, v)
+                   : kind == 1 ? ldpc_inter<int16_t, int16_t>(K, n_ite, norm, n, y, cwd + f0, v)
+                               : ldpc_tinter<int16_t, int16_t>(K, n_ite, norm, n, y, cwd + f0, v);
+        });
+    }
+
     // Galois tables + generator polynomial (Galois.cpp:158-183, BCH_polynomial_generator.cpp:52-139)
     int ref_bch_tables(int* alpha_to, int* index_of, int* g, int* g_len)
     {
@@ -158,6 +253,17 @@ extern "C"
         for (int f = 0; f < n_frames; f++)
             b->dec.decode_hiho(Y + (size_t)f * N, cwd + f, V + (size_t)f * K);
         return 0;
+    }
+
+    // Decoder_BCH_DVBS2 over n_threads instances (each allocates its own 1.07 GB elp table)
+    int ref_bch_decode_mt(int K, int N, int n_frames, int n_threads, const int32_t* Y, int8_t* cwd, int32_t* V)
+    {
+        return run_mt(n_frames, n_threads, 1, [&](int f0, int n) {
+            ref_bch b(K, N);
+            for (int f = f0; f < f0 + n; f++)
+                b.dec.decode_hiho(Y + (size_t)f * N, cwd + f, V + (size_t)f * K);
+            return 0;
+        });
     }
 
     // TX side, used only to make valid codewords for tests (main.cpp:75-84 order: scramble -> BCH -> LDPC -> itl -> map)

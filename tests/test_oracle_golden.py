@@ -157,3 +157,48 @@ def test_framer_and_estimator_match_reference(oracle, modcod):
     ref = g[k + "_est"]
     assert np.max(np.abs(sig - ref[0]) / ref[0]) < 3e-6
     assert np.allclose(eb, ref[1], rtol=0, atol=1e-4) and np.allclose(es, ref[2], rtol=0, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ 256 frames per MODCOD
+def load256(oracle, modcod):
+    """tests/golden/ldpc256_<modcod>.npz (reference outputs, make_golden_ldpc.py) + its regenerated inputs."""
+    import sys
+
+    sys.path.insert(0, GOLD)
+    import ldpc_inputs as gi
+
+    g = np.load(os.path.join(GOLD, "ldpc256_%s.npz" % modcod.replace("/", "_")))
+    d = gi.make(oracle, modcod, seed=int(g["seed"]))
+    q16, q8 = gi.quantize(d["llr"], 2, 6), gi.quantize(d["llr"], 1, 6).astype(np.int8)
+    # the inputs are rebuilt from integer hashing + IEEE float32 add/mul/min: a mismatch means numpy changed, not the decoder
+    assert gi.sha(d["llr"]) == str(g["llr_sha"]) and gi.sha(q16) == str(g["q16_sha"]) and gi.sha(q8) == str(g["q8_sha"])
+    N, K = MODCODS[modcod]["N_bch"], MODCODS[modcod]["K_bch"]
+    want = {k[:-2]: ub(g[k], N) ^ d["ldpc"][:, :N] for k in g.files if k.endswith("_x") and k != "bch_x"}
+    want["bch"] = ub(g["bch_x"], K) ^ d["bch"][:, :K]
+    return g, d, q16, q8, want
+
+
+@pytest.mark.parametrize("modcod", ALL)
+def test_ldpc_256_frames_across_the_waterfall(oracle, modcod):
+    """Oracle == sequential reference decoders (float, int16, int8: bits and CWD on all 256 frames, FER ~1 -> 0), == both
+    inter-frame SIMD decoders (ONMS_inter, row a8; templated ..._inter<Update_rule_NMS_simd>, row a9) on every frame
+    those report as converged, and the BCH stage behind it."""
+    g, d, q16, q8, want = load256(oracle, modcod)
+    N, K = MODCODS[modcod]["N_bch"], MODCODS[modcod]["K_bch"]
+    thr = os.cpu_count() or 4
+    V, cwd, nit = oracle.ldpc_decode_mt(N, d["llr"], thr)
+    assert np.array_equal(V, want["seq_f32"]) and np.array_equal(cwd, g["seq_f32_cwd"]) and np.array_equal(nit, g["seq_f32_nit"])
+    assert 0 < (cwd == 0).sum() < 256 and nit.min() < 10  # the set really spans failing and early-stopping frames
+    for key in ("onms_f32", "tint_f32"):
+        ok = g[key + "_cwd"] == 1
+        assert ok.sum() >= 64 and np.array_equal(V[ok], want[key][ok]) and (cwd[ok] == 1).all()
+    assert np.array_equal(g["onms_f32_cwd"], g["tint_f32_cwd"]) and np.array_equal(want["onms_f32"], want["tint_f32"])
+    V16, c16, _ = oracle.ldpc_decode_mt(N, q16, thr, prec="i16")
+    assert np.array_equal(V16, want["seq_i16"]) and np.array_equal(c16, g["seq_i16_cwd"])
+    for key in ("onms_i16", "tint_i16"):
+        ok = g[key + "_cwd"] == 1
+        assert np.array_equal(V16[ok], want[key][ok])
+    V8, c8, _ = oracle.ldpc_decode_mt(N, q8, thr, prec="i8")
+    assert np.array_equal(V8, want["seq_i8"]) and np.array_equal(c8, g["seq_i8_cwd"])
+    Vb, cb, _ = oracle.bch_decode(K, N, V)
+    assert np.array_equal(Vb, want["bch"]) and np.array_equal(cb, g["bch_cwd"])

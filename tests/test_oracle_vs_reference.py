@@ -111,3 +111,43 @@ def test_framer_and_estimator(oracle, ref, modcod):
     eo, er = oracle.estimate(n_sym, mc["K_bch"], mc["bps"], a), ref.estimate(n_sym, mc["K_bch"], mc["bps"], a)
     assert np.max(np.abs(eo[0] - er[0]) / er[0]) < 3e-6
     assert np.allclose(eo[1], er[1], rtol=0, atol=1e-4) and np.allclose(eo[2], er[2], rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("modcod", ["QPSK-S_8/9", "QPSK-S_3/5"])
+def test_ldpc_templated_inter_decoder(oracle, ref, modcod):
+    """Decoder_LDPC_BP_horizontal_layered_inter<B,R,Update_rule_NMS_simd<R>> (what AFF3CT's factory builds
+    for --dec-simd INTER in C++17 builds) against the oracle, float and int16: identical on every frame it reports as
+    converged, and identical to ONMS_inter (a8) altogether."""
+    N = MODCODS[modcod]["N_bch"]
+    _, nat = _nat_llrs(oracle, ref, modcod, 64, seed=21)
+    V, cwd, _ = oracle.ldpc_decode(N, nat)
+    Vt, ct = ref.ldpc_decode(N, nat, simd="tinter")
+    Vi, ci = ref.ldpc_decode(N, nat, simd=True)
+    ok = ct == 1
+    assert ok.sum() > 8 and np.array_equal(V[ok], Vt[ok]) and (cwd[ok] == 1).all()
+    assert np.array_equal(Vt, Vi) and np.array_equal(ct, ci)
+    for norm in (1.0, 0.75):
+        q = ref.quantize(nat, 2, 6, "i16")
+        Vq, cq, _ = oracle.ldpc_decode(N, q, prec="i16", norm=norm)
+        Vt, ct = ref.ldpc_decode(N, q, prec="i16", simd="tinter", norm=norm)
+        ok = ct == 1
+        assert ok.sum() > 8 and np.array_equal(Vq[ok], Vt[ok])
+
+
+def test_ldpc_without_syndrome_reports_every_frame_valid(oracle, ref):
+    """enable_syndrome = false: the reference never tests the syndrome, returns status 0 and CWD = 1 for every frame
+    (Decoder_LDPC_BP.hxx:8-20); the oracle (and the GPU path with early_stop = 0) mirror that."""
+    _, nat = _nat_llrs(oracle, ref, "QPSK-S_8/9", 16, seed=22)
+    Vr, cr = ref.ldpc_decode(14400, nat, n_ite=4, enable_syndrome=False)
+    V, cwd, nit = oracle.ldpc_decode(14400, nat, n_ite=4, early_stop=False)
+    assert (cr == 1).all() and np.array_equal(cwd, cr) and np.array_equal(V, Vr) and (nit == 4).all()
+
+
+def test_multithreaded_reference_drivers_equal_the_single_threaded_ones(oracle, ref):
+    _, nat = _nat_llrs(oracle, ref, "QPSK-S_8/9", 48, seed=23)
+    a = ref.ldpc_decode(14400, nat)
+    b = ref.ldpc_decode(14400, nat, threads=5)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    c = ref.bch_decode(14232, 14400, a[0][:6], threads=2)
+    d = ref.bch_decode(14232, 14400, a[0][:6])
+    assert np.array_equal(c[0], d[0]) and np.array_equal(c[1], d[1])
