@@ -7,8 +7,12 @@ One "step" = one pass of the fused chain (dvbs2_cuda_chain_dev) over one batch o
 `value`  = info Mbit/s (K_bch * frames / time, the reference's throughput definition, D/mains/TX_RX_BB/main.cpp:130) with
            the received symbols already resident in HBM; whole-job aggregate over all ranks (frames shard by batch, no
            collective on the data path; NCCL only reduces the time and the FER counters).
-`e2e`    = the same metric through the host-buffer C-ABI call (dvbs2_cuda_chain) with pinned HOST buffers: H2D of the
-           symbols and D2H of the int32 bits inside the timed region.
+`e2e`    = the same metric through the host-buffer C-ABI calls with pinned HOST buffers, H2D of the symbols and D2H of the
+           payload inside the timed region, driven like a replicated StreamPU stage (module clones on host threads).  Measured
+           per socket format (`e2e.sockets`): the reference's own socket types (float I/Q in, int32 per bit out: 121.7 KB per
+           frame, PCIe-bound near 11 Gbit/s on any GPU) and the compact formats of SURVEY §8f N2 (sc16 / sc8 I/Q in, packed
+           bytes out).  `e2e.value` is the sc16-in / packed-out stage: bit-identical to the float sockets for the same
+           sample values (tests/test_gpu_compact_sockets.py), i.e. what a radio that delivers sc16 feeds the stage.
 `roofline` = the LDPC kernel (dominant), algorithmic bytes per frame from SURVEY.md §8(d) / DESIGN.md §5.
 `cpu_baseline` = the compiled reference chain (oracle/_ref, AVX-512 ONMS_inter -F 16 + Modem_generic_fast + BCH_std) on
            this box's host cores, bounded sample; `--impl reference` times just that.
@@ -48,8 +52,11 @@ def parse():
     p.add_argument("--prec", default="f32", choices=["f32", "i16", "i8"])
     p.add_argument("--ite", type=int, default=10)
     p.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the largest of 3, 2, 1 waves of the LDPC kernel = SMs x 12 warps x 64 frames each that fits in 80 %% of the free HBM)")
-    p.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e step per GPU (default: one wave)")
+    p.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e step per GPU over all clones (default: two waves; one for the float/int32 sockets)")
     p.add_argument("--e2e-clones", type=int, default=4)
+    p.add_argument("--e2e-sockets", default="", help="comma list of socket formats to time (default: f32_int32,f32_packed,sc16_packed,sc8_packed; llr8_packed with --prec i16)")
+    p.add_argument("--no-configs", action="store_true", help="skip the extra lines for BASELINE configs 2-4")
+    p.add_argument("--no-numa", action="store_true", help="do not bind this rank to the CPU cores next to its GPU")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-int16", action="store_true", help="skip the extra fixed-point (int16) line of the same workload")
@@ -123,6 +130,30 @@ def host_threads(args):
     except Exception:
         pass
     return n
+
+
+def numa_bind(gpu_index):
+    """Bind this process (and so its pinned staging buffers, first touch) to the CPU cores next to its GPU: with one rank per
+    GPU the ranks' host traffic then spreads over all sockets' memory controllers instead of piling up on node 0."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        hd = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(hd, n)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"bound": False, "why": "empty affinity mask"}
+        os.sched_setaffinity(0, cpus)
+        node = None
+        for d in sorted(os.listdir("/sys/devices/system/node")) if os.path.isdir("/sys/devices/system/node") else []:
+            if d.startswith("node") and os.path.exists("/sys/devices/system/node/%s/cpu%d" % (d, min(cpus))):
+                node = int(d[4:])
+        return {"bound": True, "cpus": len(cpus), "numa_node": node}
+    except Exception as e:  # noqa: BLE001
+        return {"bound": False, "why": repr(e)[:120]}
 
 
 def cpu_reference_run(modcod, ite, sigma, sym, seconds, threads):
@@ -200,7 +231,8 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from dvbs2_b200 import Decoder_chain_DVBS2_cuda, Handle, Transmitter_DVBS2_cuda, synth
+    from dvbs2_b200 import (Decoder_chain_compact_DVBS2_cuda, Decoder_chain_DVBS2_cuda, Decoder_llr8_DVBS2_cuda, Handle,
+                            Modem_DVBS2_cuda, Transmitter_DVBS2_cuda, synth)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -209,6 +241,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = {"bound": False, "why": "--no-numa"} if args.no_numa else numa_bind(local)
     real_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -348,80 +381,132 @@ def main():
 
     # ---- end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside the timed region).
     # Driven the way StreamPU drives a replicated stage: NC module clones (one handle + streams each), one host thread
-    # per clone calling the synchronous task; copies of one clone overlap the kernels of the others.
+    # per clone calling the synchronous task; copies of one clone overlap the kernels of the others.  One run per socket
+    # format; the clones of a format are created, timed and destroyed before the next format allocates its buffers.
     e2e = None
     if not args.no_e2e:
         NC = max(1, args.e2e_clones)
-        Fe = max(256, min(F, args.e2e_frames if args.e2e_frames > 0 else wave) // NC // 256 * 256)
-        clones = []
-        for c in range(NC):
-            hc = Handle(modcod=modcod, n_ite=args.ite, norm=1.0, precision=args.prec, early_stop=True, n_frames=Fe, device=local,
-                        **tune)
-            hs = torch.empty(Fe, dtype=torch.float32).pin_memory()
-            hx = torch.empty((Fe, 2 * n_sym), dtype=torch.float32).pin_memory()
-            hV = torch.empty((Fe, K_bch), dtype=torch.int32).pin_memory()
-            hc1, hc2 = torch.empty(Fe, dtype=torch.int8).pin_memory(), torch.empty(Fe, dtype=torch.int8).pin_memory()
-            hn = torch.empty(Fe, dtype=torch.int32).pin_memory()
-            hP = torch.empty((Fe, K_bch // 8), dtype=torch.uint8).pin_memory()
-            hs.copy_(batches[0][0][c * Fe:(c + 1) * Fe])
-            hx.copy_(batches[0][1][c * Fe:(c + 1) * Fe])
-            clones.append((hc, Decoder_chain_DVBS2_cuda(hc, Fe), [t.numpy() for t in (hs, hx, hc1, hc2, hV, hn)],
-                           (hs, hx, hV, hc1, hc2, hn, hP)))
-        torch.cuda.synchronize()
+        default_fmts = "llr8_packed" if args.prec == "i16" else "f32_int32,f32_packed,sc16_packed,sc8_packed"
+        fmts = [f for f in (args.e2e_sockets or default_fmts).split(",") if f]
+        SC16, SC8 = 1.0 / 8192, 1.0 / 32  # LSB of the integer I/Q formats: +-4.0 full scale (unit-energy constellations)
+        pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()  # noqa: E731
 
-        def run_clones(n, packed=False):
-            def work(c):
-                _, che, a, keep = clones[c]
-                for _ in range(n):
-                    if packed:  # bit-packed, descrambled payload bytes out instead of int32 per bit
-                        che.demodulate_decode_packed(a[0], a[1], a[2], a[3], keep[6].numpy(), a[5], descramble=True)
-                    else:
-                        che.demodulate_decode(*a)
-            ths = [threading.Thread(target=work, args=(c,)) for c in range(NC)]
-            for t in ths:
-                t.start()
-            for t in ths:
-                t.join()
+        def e2e_run(fmt):
+            in_kind, out_kind = fmt.split("_")
+            # frames per step over all clones: two waves for the compact formats, one for the float / int32 sockets (19 GB of
+            # pinned memory per wave there)
+            waves = 1 if fmt == "f32_int32" else 2
+            Fe = max(256, min(F, args.e2e_frames if args.e2e_frames > 0 else waves * wave) // NC // 256 * 256)
+            prec = "i16" if in_kind == "llr8" else args.prec
+            clones, same = [], None
+            for c in range(NC):
+                hc = Handle(modcod=modcod, n_ite=args.ite, norm=1.0, precision=prec, early_stop=True, n_frames=Fe, device=local, **tune)
+                src_sig, src_rx = batches[0][0][c * Fe:(c + 1) * Fe], batches[0][1][c * Fe:(c + 1) * Fe]
+                hs = pin(Fe, dtype=torch.float32)
+                hs.copy_(src_sig)
+                hc1, hc2, hn = pin(Fe, dtype=torch.int8), pin(Fe, dtype=torch.int8), pin(Fe, dtype=torch.int32)
+                if in_kind == "f32":
+                    hx = pin(Fe, 2 * n_sym, dtype=torch.float32)
+                    hx.copy_(src_rx)
+                elif in_kind in ("sc16", "sc8"):  # the radio's ADC words: quantised once, outside the timed region
+                    sc, lim, dt = (SC16, 32767, torch.int16) if in_kind == "sc16" else (SC8, 127, torch.int8)
+                    hx = pin(Fe, 2 * n_sym, dtype=dt)
+                    q = src_rx * (1.0 / sc)
+                    hx.copy_((torch.sign(q) * torch.floor(torch.abs(q) + 0.5)).clamp_(-lim, lim).to(dt))
+                else:  # llr8: Quantizer_pow2(6, 2) outputs of the demapper's LLRs, one int8 per LLR
+                    hx = pin(Fe, N_LDPC, dtype=torch.int8)
+                    llr = torch.empty((Fe, N_LDPC), dtype=torch.float32, device=dev)
+                    hf = Handle(modcod=modcod, n_frames=Fe, device=local)
+                    torch.cuda.synchronize()
+                    Modem_DVBS2_cuda(hf, Fe).demodulate_dev(src_sig.contiguous(), src_rx.contiguous(), llr, deinterleave=True)
+                    hf.sync()
+                    hf.close()
+                    q = llr * 4.0
+                    hx.copy_((torch.sign(q) * torch.floor(torch.abs(q) + 0.5)).clamp_(-31, 31).to(torch.int8))
+                    del llr
+                hV = pin(Fe, K_bch, dtype=torch.int32) if out_kind == "int32" else pin(Fe, K_bch // 8, dtype=torch.uint8)
+                a = dict(sig=hs.numpy(), x=hx.numpy(), c1=hc1.numpy(), c2=hc2.numpy(), n=hn.numpy(), V=hV.numpy())
+                if in_kind == "f32":
+                    m = Decoder_chain_DVBS2_cuda(hc, Fe)
+                    call = ((lambda m=m, a=a: m.demodulate_decode(a["sig"], a["x"], a["c1"], a["c2"], a["V"], a["n"]))
+                            if out_kind == "int32" else
+                            (lambda m=m, a=a: m.demodulate_decode_packed(a["sig"], a["x"], a["c1"], a["c2"], a["V"], a["n"], descramble=True)))
+                elif in_kind == "llr8":
+                    m = Decoder_llr8_DVBS2_cuda(hc, Fe)
+                    call = lambda m=m, a=a: m.decode(a["x"], a["c1"], a["c2"], V_K_packed=a["V"], n_iter=a["n"], descramble=True)  # noqa: E731
+                else:
+                    m = Decoder_chain_compact_DVBS2_cuda(hc, Fe, in_kind, SC16 if in_kind == "sc16" else SC8)
+                    call = lambda m=m, a=a: m.demodulate_decode(a["sig"], a["x"], a["c1"], a["c2"], V_K_packed=a["V"], n_iter=a["n"], descramble=True)  # noqa: E731
+                clones.append((hc, call, a, (hs, hx, hV, hc1, hc2, hn)))
+            torch.cuda.synchronize()
 
-        run_clones(max(1, min(args.warmup, 2)))
-        for hc, _, _, _ in clones:
-            hc.reset_stats()
-        barrier()
-        torch.cuda.synchronize()
-        w0 = time.perf_counter()
-        run_clones(args.steps)
-        torch.cuda.synchronize()
-        w = time.perf_counter() - w0
-        w = reduce_([w], dist.ReduceOp.MAX if world > 1 else None)[0]
-        barrier()
-        e2e_launches = sum(hc.stats()["kernel_launches"] for hc, _, _, _ in clones)
-        # the host result of clone 0 equals the device-resident result of the same frames
-        step(0)
-        h.sync()
-        same = bool(np.array_equal(clones[0][2][4], V[:Fe].cpu().numpy()))
-        e2e = {"value": round(K_bch * Fe * NC * args.steps * world / w / 1e6, 2), "unit": "Mbit/s",
-               "h2d_bytes_per_step": int(NC * (Fe * 4 + Fe * 2 * n_sym * 4)),
-               "d2h_bytes_per_step": int(NC * (Fe * K_bch * 4 + 2 * Fe + Fe * 4)), "frames_per_step_per_gpu": Fe * NC,
-               "clones": NC, "ms_per_step": round(w / args.steps * 1e3, 3), "gpu_launches": int(e2e_launches),
-               "matches_device_path": same,
-               "api": "dvbs2_cuda_chain (host pointers, pinned), %d concurrent module clones x %d frames" % (NC, Fe)}
-        # the same stage with the bit-packed output format (1/32 of the D2H bytes); not the headline: other socket types
-        run_clones(1, packed=True)
-        barrier()
-        torch.cuda.synchronize()
-        w0 = time.perf_counter()
-        run_clones(args.steps, packed=True)
-        torch.cuda.synchronize()
-        wp = time.perf_counter() - w0
-        wp = reduce_([wp], dist.ReduceOp.MAX if world > 1 else None)[0]
-        barrier()
-        e2e["packed_output"] = {"value": round(K_bch * Fe * NC * args.steps * world / wp / 1e6, 2), "unit": "Mbit/s",
-                                "d2h_bytes_per_step": int(NC * (Fe * (K_bch // 8) + 2 * Fe + Fe * 4)),
-                                "ms_per_step": round(wp / args.steps * 1e3, 3),
-                                "api": "dvbs2_cuda_chain_packed (descrambled payload, 8 bits per byte)"}
-        for hc, _, _, _ in clones:
-            hc.close()
-        del clones
+            def run_clones(n):
+                def work(c):
+                    for _ in range(n):
+                        clones[c][1]()
+                ths = [threading.Thread(target=work, args=(c,)) for c in range(NC)]
+                for t in ths:
+                    t.start()
+                for t in ths:
+                    t.join()
+
+            run_clones(max(1, min(args.warmup, 2)))
+            for hc, _, _, _ in clones:
+                hc.reset_stats()
+            barrier()
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            run_clones(args.steps)
+            torch.cuda.synchronize()
+            w = time.perf_counter() - w0
+            w = reduce_([w], dist.ReduceOp.MAX if world > 1 else None)[0]
+            barrier()
+            n_launch = sum(hc.stats()["kernel_launches"] for hc, _, _, _ in clones)
+            fails = sum(int((a["c2"] == 0).sum()) for _, _, a, _ in clones)
+            if fmt == "f32_int32":  # the host result of clone 0 equals the device-resident result of the same frames
+                step(0)
+                h.sync()
+                same = bool(np.array_equal(clones[0][2]["V"], V[:Fe].cpu().numpy()))
+            in_b = clones[0][2]["x"].nbytes + clones[0][2]["sig"].nbytes
+            out_b = clones[0][2]["V"].nbytes + 2 * Fe + 4 * Fe
+            for hc, _, _, _ in clones:
+                hc.close()
+            del clones
+            r = {"value": round(K_bch * Fe * NC * args.steps * world / w / 1e6, 2), "unit": "Mbit/s",
+                 "h2d_bytes_per_step": int(NC * in_b), "d2h_bytes_per_step": int(NC * out_b),
+                 "bytes_per_frame": {"h2d": round(in_b / Fe, 1), "d2h": round(out_b / Fe, 1)},
+                 "host_gbs_per_gpu": round(NC * (in_b + out_b) * args.steps / w / 1e9, 2),
+                 "host_gbs_total": round(world * NC * (in_b + out_b) * args.steps / w / 1e9, 2),
+                 "frames_per_step_per_gpu": Fe * NC, "clones": NC, "ms_per_step": round(w / args.steps * 1e3, 3),
+                 "gpu_launches": int(n_launch), "bch_fer": round(fails / (Fe * NC), 5)}
+            if same is not None:
+                r["matches_device_path"] = same
+            return r
+
+        API = {"f32_int32": "dvbs2_cuda_chain: float I/Q in, int32 per bit out (the reference's socket types)",
+               "f32_packed": "dvbs2_cuda_chain_packed: float I/Q in, descrambled payload bytes out",
+               "sc16_packed": "dvbs2_cuda_chain_compact: sc16 I/Q in (LSB 2^-13), descrambled payload bytes out",
+               "sc8_packed": "dvbs2_cuda_chain_compact: sc8 I/Q in (LSB 2^-5), descrambled payload bytes out",
+               "llr8_packed": "dvbs2_cuda_decode_llr8: int8 LLRs in (Quantizer_pow2 6/2), int16 decoder, payload bytes out"}
+        socks = {}
+        for fmt in fmts:
+            try:
+                socks[fmt] = e2e_run(fmt)
+                socks[fmt]["api"] = API.get(fmt, fmt)
+            except Exception as e:  # noqa: BLE001
+                socks[fmt] = {"value": None, "error": repr(e)[:300]}
+            torch.cuda.empty_cache()
+        head = next((f for f in ("sc16_packed", "llr8_packed", "f32_packed", "f32_int32") if socks.get(f, {}).get("value")), None)
+        if head:
+            e2e = dict(socks[head])
+            e2e["headline_sockets"] = head
+            e2e["api"] = API.get(head, head) + "; %d concurrent module clones (host threads) x %d frames per call" % (
+                NC, e2e["frames_per_step_per_gpu"] // NC)
+            e2e["vs_device_resident"] = round(e2e["value"] / value, 4)
+            e2e["host_numa"] = numa
+            e2e["sockets"] = socks
+            if "f32_int32" in socks:
+                e2e["matches_device_path"] = socks["f32_int32"].get("matches_device_path")
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the compiled reference on this box's host cores, bounded sample
     cpu = None
@@ -440,25 +525,47 @@ def main():
     # ---- the same workload through the fixed-point (int16, bit-exact vs AFF3CT's int16 decoder) kernel, device-resident only:
     # a separate process after this one released its HBM (N = 1 runs only; the headline stays the float path the dvbs2
     # binaries run)
-    int16 = None
-    if rank == 0 and world == 1 and args.prec == "f32" and not args.no_int16:
+    int16, configs = None, None
+    if rank == 0 and world == 1 and args.prec == "f32" and (not args.no_int16 or not args.no_configs):
         h.close()
         h = None
         del batches, V, chain, tx, sig, rx  # sig / rx: the loop variables still hold the last input batch
         torch.cuda.empty_cache()
-        try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--prec", "i16", "--workload", args.workload,
-                                "--ite", str(args.ite), "--steps", str(max(3, args.steps // 2)), "--warmup", "3", "--no-e2e",
-                                "--no-cpu", "--no-int16"] + (["--ebn0", str(args.ebn0)] if args.ebn0 is not None else []),
-                               capture_output=True, text=True, timeout=600)
-            d = json.loads(r.stdout.strip().splitlines()[-1])
-            int16 = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
-                     "frames_per_step_per_gpu": d["config"]["frames_per_step_per_gpu"], "stage_ms": d["stage_ms"],
-                     "quantizer": "Quantizer_pow2 6 bits, 2 fractional (AFF3CT LDPC defaults)",
-                     "message_passing": d["roofline"]["message_passing"], "mean_iterations": d["fer"]["mean_iterations"],
-                     "ldpc_fer": d["fer"]["ldpc_fer"], "bch_fer": d["fer"]["bch_fer"], "gpu_launches": d["gpu_launches"]}
-        except Exception as e:  # noqa: BLE001
-            int16 = {"value": None, "error": repr(e)[:300]}
+
+        def sub(workload, prec, extra):
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--prec", prec, "--workload", workload,
+                                "--ite", str(args.ite), "--steps", str(max(3, args.steps // 2)), "--warmup", "3", "--no-cpu",
+                                "--no-int16", "--no-configs"] + extra, capture_output=True, text=True, timeout=900)
+            return json.loads(r.stdout.strip().splitlines()[-1])
+
+        def brief(d):
+            return {"value": d["value"], "unit": d["unit"], "dtype": d["dtype"], "workload": d["config"]["workload"],
+                    "ms_per_step": d["ms_per_step"], "frames_per_step_per_gpu": d["config"]["frames_per_step_per_gpu"],
+                    "stage_ms": d["stage_ms"], "mean_iterations": d["fer"]["mean_iterations"], "ldpc_fer": d["fer"]["ldpc_fer"],
+                    "bch_fer": d["fer"]["bch_fer"], "monitor_fer": d["fer"]["monitor"]["fer"], "gpu_launches": d["gpu_launches"],
+                    "roofline": {k: d["roofline"][k] for k in ("achieved", "peak", "frac", "kernel_ms", "kernel_share_of_step",
+                                                               "algorithmic_bytes_per_frame", "message_passing")}}
+
+        if not args.no_int16:
+            try:  # the headline workload through the packed int16 kernel + the int8-LLR socket end to end
+                d = sub(args.workload, "i16", (["--ebn0", str(args.ebn0)] if args.ebn0 is not None else []) +
+                        ["--e2e-sockets", "llr8_packed", "--e2e-clones", str(args.e2e_clones)])
+                int16 = brief(d)
+                int16["quantizer"] = "Quantizer_pow2 6 bits, 2 fractional (AFF3CT LDPC defaults)"
+                int16["message_passing"] = d["roofline"]["message_passing"]
+                int16["e2e"] = d.get("e2e")
+            except Exception as e:  # noqa: BLE001
+                int16 = {"value": None, "error": repr(e)[:300]}
+        if not args.no_configs and args.workload == "qpsk89":
+            # BASELINE.json configs 2-4, device-resident: QPSK-S_3/5 at the waterfall (all iterations active), 8PSK-S_3/5 float and
+            # fixed point, 8PSK-S_8/9 at high Eb/N0 (divergent iteration counts)
+            configs = {}
+            for name, wl_, prec in (("qpsk35_f32", "qpsk35", "f32"), ("qpsk35_i16", "qpsk35", "i16"), ("8psk35_f32", "8psk35", "f32"),
+                                    ("8psk35_i16", "8psk35", "i16"), ("8psk89_f32", "8psk89", "f32")):
+                try:
+                    configs[name] = brief(sub(wl_, prec, ["--no-e2e"]))
+                except Exception as e:  # noqa: BLE001
+                    configs[name] = {"value": None, "error": repr(e)[:300]}
 
     if rank == 0:
         out = {
@@ -471,7 +578,7 @@ def main():
                        "l2": "inputs %.1f GB per step >> 126 MB L2, %d batches rotated" % (F * 2 * n_sym * 4 / 1e9, NB),
                        "parallelism": "frames sharded by batch, %d rank(s), no data-path collective" % world},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "stage_ms": stage_ms, "int16": int16,
+            "stage_ms": stage_ms, "int16": int16, "configs": configs, "iter_hist": st["iter_hist"][:args.ite + 1],
             "fer": {"frames": int(cnt[0]), "ldpc_fer": cnt[2] / max(1, cnt[0]), "bch_fer": cnt[3] / max(1, cnt[0]),
                     "mean_iterations": cnt[1] / max(1, cnt[0]),
                     "monitor": {"frames": int(mon[0]), "bit_errors": int(mon[1]), "frame_errors": int(mon[2]),

@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("DVBS2_CUDA_LIB") or os.path.join(HERE, "libdvbs2_cuda
 N_LDPC = 16200
 OK, ERR_INVALID, ERR_CUDA, ERR_TOO_MANY, ERR_NOMEM = 0, -1, -2, -3, -4
 PREC = {"f32": 0, "i16": 1, "i8": 2}
+IQ_FORMAT = {"f32": 0, "f16": 1, "sc16": 2, "sc8": 3}  # dvbs2_iq_format
 MODCOD = {"QPSK-S_8/9": 0, "QPSK-S_3/5": 1, "8PSK-S_3/5": 2, "8PSK-S_8/9": 3, "16APSK-S_8/9": 4}
 
 # every symbol include/dvbs2_cuda.h declares (tests check the library exports all of them)
@@ -25,7 +26,8 @@ SYMBOLS = [
     "dvbs2_cuda_tx_set_payload", "dvbs2_cuda_tx_random_payload", "dvbs2_cuda_tx_modulate_awgn_dev", "dvbs2_cuda_tx_get_bits",
     "dvbs2_cuda_monitor_check", "dvbs2_cuda_monitor_get", "dvbs2_cuda_chain_packed", "dvbs2_cuda_chain_packed_dev",
     "dvbs2_cuda_pl_frame_size", "dvbs2_cuda_remove_plh", "dvbs2_cuda_remove_plh_dev", "dvbs2_cuda_estimate",
-    "dvbs2_cuda_estimate_dev", "dvbs2_cuda_rx_chain", "dvbs2_cuda_rx_chain_dev",
+    "dvbs2_cuda_estimate_dev", "dvbs2_cuda_rx_chain", "dvbs2_cuda_rx_chain_dev", "dvbs2_cuda_iq_frame_bytes",
+    "dvbs2_cuda_chain_compact", "dvbs2_cuda_chain_compact_dev", "dvbs2_cuda_decode_llr8", "dvbs2_cuda_decode_llr8_dev",
 ]
 
 
@@ -44,7 +46,7 @@ class Info(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("frames", "ldpc_iterations", "ldpc_failures", "bch_nonzero", "bch_failures",
-                                          "kernel_launches")]
+                                          "kernel_launches")] + [("iter_hist", C.c_uint64 * 33)]
 
 
 class Timers(C.Structure):
@@ -113,6 +115,12 @@ def load():
     L.dvbs2_cuda_estimate_dev.argtypes = [vp, vp, vp, vp, vp, ip]
     L.dvbs2_cuda_rx_chain.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ip, vp, ip]
     L.dvbs2_cuda_rx_chain_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ip, vp, ip]
+    L.dvbs2_cuda_iq_frame_bytes.argtypes = [vp, ip, ip]
+    L.dvbs2_cuda_iq_frame_bytes.restype = C.c_size_t
+    L.dvbs2_cuda_chain_compact.argtypes = [vp, ip, C.c_float, vp, vp, vp, vp, vp, vp, vp, ip, vp, ip, ip]
+    L.dvbs2_cuda_chain_compact_dev.argtypes = [vp, ip, C.c_float, vp, vp, vp, vp, vp, vp, vp, ip, vp, ip, ip]
+    L.dvbs2_cuda_decode_llr8.argtypes = [vp, vp, vp, vp, vp, vp, ip, vp, ip]
+    L.dvbs2_cuda_decode_llr8_dev.argtypes = [vp, vp, vp, vp, vp, vp, ip, vp, ip]
     L.dvbs2_cuda_tx_set_payload.argtypes = [vp, vp, ip]
     L.dvbs2_cuda_tx_random_payload.argtypes = [vp, C.c_uint64, ip]
     L.dvbs2_cuda_tx_modulate_awgn_dev.argtypes = [vp, C.c_float, C.c_uint64, vp, vp, ip]

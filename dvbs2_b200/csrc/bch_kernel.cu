@@ -373,17 +373,17 @@ launch_bch_decode(const BchLaunch& a, const BchDevTables& t, cudaStream_t s)
     if (a.n_groups <= 2048)
     { // up to 65536 frames: the segmented division (short dependency chain)
         const dim3 grid((a.n_groups + 3) / 4, BCH_NPOLY);
-        bch_remainder_kernel<<<grid, 128, 0, s>>>(a);
+        bch_remainder_kernel<<<grid, 128, 0, s>>>(a); count_launch();
     }
     else
     {
         const dim3 grid((a.n_groups + 127) / 128, BCH_NPOLY);
-        bch_remainder_serial_kernel<<<grid, 128, 0, s>>>(a);
+        bch_remainder_serial_kernel<<<grid, 128, 0, s>>>(a); count_launch();
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int blocks = (a.n_frames + BCH_FRAMES_PER_BLOCK - 1) / BCH_FRAMES_PER_BLOCK;
-    bch_correct_kernel<<<blocks, BCH_FRAMES_PER_BLOCK * 32, 0, s>>>(a, t);
+    bch_correct_kernel<<<blocks, BCH_FRAMES_PER_BLOCK * 32, 0, s>>>(a, t); count_launch();
     return cudaGetLastError();
 }
 } // namespace dvbs2

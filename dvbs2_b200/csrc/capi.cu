@@ -15,6 +15,12 @@
 namespace dvbs2
 {
 bool bch_minpoly_matches(const BchTables& t); // bch_kernel.cu
+uint64_t&
+launch_counter()
+{
+    static thread_local uint64_t n = 0;
+    return n;
+}
 }
 using namespace dvbs2;
 
@@ -115,6 +121,22 @@ fail_cuda(dvbs2_cuda_handle* h, cudaError_t e, const char* what)
     cudaGetLastError(); // clear sticky-less errors
     return e == cudaErrorMemoryAllocation ? DVBS2_ERR_NOMEM : DVBS2_ERR_CUDA;
 }
+
+// credits the kernels launched by this thread during an API call to the handle the call works on
+struct LaunchScope
+{
+    dvbs2_cuda_handle* h;
+    uint64_t at;
+    explicit LaunchScope(dvbs2_cuda_handle* hh)
+      : h(hh)
+      , at(launch_counter())
+    {
+    }
+    ~LaunchScope()
+    {
+        if (h) h->launches += launch_counter() - at;
+    }
+};
 
 #define CU(h, call)                                                                                                    \
     do                                                                                                                 \
@@ -258,9 +280,11 @@ bch_args(dvbs2_cuda_handle* h, int first_frame, int n_frames, int8_t* cwd)
 }
 
 DemapLaunch
-demap_args(dvbs2_cuda_handle* h, const float* d_sigma, const float* d_sym, int n_frames, bool pl_frames = false)
+demap_args(dvbs2_cuda_handle* h, const float* d_sigma, const float* d_sym, int n_frames, bool pl_frames = false,
+           int iq_fmt = DVBS2_IQ_F32, float iq_scale = 1.f)
 {
     DemapLaunch d{};
+    d.sym_fmt = iq_fmt, d.iq_scale = iq_scale;
     d.pl_sym = pl_frames ? pl_frame_symbols(h->mc.n_sym) : 0;
     d.sigma = d_sigma, d.sym = d_sym, d.cstl = h->d_cstl, d.n_frames = n_frames;
     d.bps = h->mc.bps, d.n_sym = h->mc.n_sym, d.itl_cols = h->mc.itl_cols, d.itl_rev = h->mc.itl_rev;
@@ -298,14 +322,12 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
     if (call_coop(h, n_frames, nf0))
     {
         CU(h, launch_ldpc_decode_coop(a, s));
-        h->launches += 1;
         return DVBS2_OK;
     }
     const bool multi = h->rounds > 1 && h->ext_cap > 0 && h->cfg.early_stop && h->cfg.n_ite >= 4 && a.n_groups >= 2;
     if (!multi)
     {
         CU(h, launch_ldpc_decode(a, h->cfg.precision, s));
-        h->launches += 1;
         return DVBS2_OK;
     }
     int slot = 0;
@@ -324,7 +346,6 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
     a.surv_mask = mask0;
     a.surv_iters = (int*)h->surv_iters.p + first_frame;
     CU(h, launch_ldpc_decode(a, h->cfg.precision, s));
-    h->launches += 1;
     LdpcLaunch prev = a;
     size_t prev_hs = (size_t)first_frame; // slot-space index of prev's slot 0
     const int* prev_frame = nullptr;
@@ -371,7 +392,6 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
         b.surv_mask = last ? nullptr : (uint32_t*)h->surv_mask.p + hs / 32;
         b.surv_iters = last ? nullptr : (int*)h->surv_iters.p + hs;
         CU(h, launch_ldpc_decode(b, h->cfg.precision, s));
-        h->launches += 4;
         prev = b, prev_hs = hs, prev_frame = c.dst_frame, prev_n_slots = c.n_surv;
         hs += cap;
         if (last) break;
@@ -379,7 +399,6 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
     MergeLaunch m{};
     m.surv_mask = mask0, m.final_loc = final_loc, m.out_hd = out_hd0, m.n_groups = n_groups0, m.nf = nf0;
     CU(h, launch_merge_back(m, s));
-    h->launches += 1;
     return DVBS2_OK;
 }
 
@@ -398,7 +417,6 @@ run_ldpc(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const void* d_Y,
     TRY(prof_mark(h, s, P_UNPACK));
     CU(h, launch_unpack_bits((uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC, d_VK, N_LDPC, h->mc.N_bch, n_frames, s));
     TRY(prof_mark(h, s, P_END));
-    h->launches += 2;
     return DVBS2_OK;
 }
 
@@ -415,26 +433,26 @@ run_bch(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const int32_t* d_
     TRY(prof_mark(h, s, P_UNPACK));
     CU(h, launch_unpack_bits(words, d_VK, N_LDPC, h->mc.K_bch, n_frames, s));
     TRY(prof_mark(h, s, P_END));
-    h->launches += 4;
     return DVBS2_OK;
 }
 
 int
 run_chain(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const float* d_sigma, const float* d_sym,
           int8_t* d_cwd_ldpc, int8_t* d_cwd_bch, int32_t* d_VK, int32_t* d_nit, int n_frames, uint8_t* d_packed = nullptr,
-          int descramble = 0, bool pl_frames = false, float* d_sigma_est = nullptr)
+          int descramble = 0, bool pl_frames = false, float* d_sigma_est = nullptr, int iq_fmt = DVBS2_IQ_F32,
+          float iq_scale = 1.f)
 {
     if (n_frames == 0) return DVBS2_OK;
     void* var = (char*)h->var.p + (size_t)first_frame * N_LDPC * h->elt;
     TRY(prof_mark(h, s, P_DEMAP));
     if (d_sigma_est)
     { // Estimator_DVBS2 in front of the demapper: sigma per frame from the frame's own payload symbols
-        CU(h, launch_estimate(demap_args(h, nullptr, d_sym, n_frames, pl_frames), h->mc.K_bch, d_sigma_est, nullptr, nullptr, s));
+        CU(h, launch_estimate(demap_args(h, nullptr, d_sym, n_frames, pl_frames, iq_fmt, iq_scale), h->mc.K_bch, d_sigma_est,
+                              nullptr, nullptr, s));
         d_sigma = d_sigma_est;
-        h->launches += 1;
     }
     const int nf = call_nf(h, n_frames);
-    CU(h, launch_demap_to_var(demap_args(h, d_sigma, d_sym, n_frames, pl_frames), var, h->cfg.precision, nf, s));
+    CU(h, launch_demap_to_var(demap_args(h, d_sigma, d_sym, n_frames, pl_frames, iq_fmt, iq_scale), var, h->cfg.precision, nf, s));
     TRY(prof_mark(h, s, P_LDPC));
     TRY(run_ldpc_core(h, s, first_frame, n_frames, d_cwd_ldpc, d_nit, nf));
     TRY(prof_mark(h, s, P_BCH));
@@ -446,8 +464,45 @@ run_chain(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const float* d_
     else
         CU(h, launch_unpack_bits(words, d_VK, N_LDPC, h->mc.K_bch, n_frames, s, descramble ? h->d_scr_bytes : nullptr));
     TRY(prof_mark(h, s, P_END));
-    h->launches += 4;
     return DVBS2_OK;
+}
+
+// int8 LLRs (compact input socket) -> int16 decoder -> BCH -> bits / packed bytes
+int
+run_llr8_chain(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const int8_t* d_llr, int8_t* d_cwd_ldpc, int8_t* d_cwd_bch,
+               int32_t* d_VK, uint8_t* d_packed, int descramble, int32_t* d_nit, int n_frames)
+{
+    if (n_frames == 0) return DVBS2_OK;
+    void* var = (char*)h->var.p + (size_t)first_frame * N_LDPC * h->elt;
+    const int nf = call_nf(h, n_frames);
+    TRY(prof_mark(h, s, P_PACK));
+    CU(h, launch_pack_llr8_as_i16(d_llr, var, n_frames, nf, s));
+    TRY(prof_mark(h, s, P_LDPC));
+    TRY(run_ldpc_core(h, s, first_frame, n_frames, d_cwd_ldpc, d_nit, nf));
+    TRY(prof_mark(h, s, P_BCH));
+    CU(h, launch_bch_decode(bch_args(h, first_frame, n_frames, d_cwd_bch), h->bch, s));
+    TRY(prof_mark(h, s, P_UNPACK));
+    const uint32_t* words = (uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC;
+    if (d_packed)
+        CU(h, launch_unpack_bytes(words, descramble ? h->d_scr_bytes : nullptr, d_packed, N_LDPC, h->mc.K_bch, n_frames, s));
+    else
+        CU(h, launch_unpack_bits(words, d_VK, N_LDPC, h->mc.K_bch, n_frames, s, descramble ? h->d_scr_bytes : nullptr));
+    TRY(prof_mark(h, s, P_END));
+    return DVBS2_OK;
+}
+
+// waits for every pipeline stream (also on the error path of the chunked host entry points: copies already queued on the
+// other streams must not outlive the call, the caller may free or reuse its buffers as soon as we return)
+int
+sync_pipes(dvbs2_cuda_handle* h)
+{
+    int rc = DVBS2_OK;
+    for (int i = 0; i < N_PIPE; i++)
+    {
+        const cudaError_t e = cudaStreamSynchronize(h->pipe[i]);
+        if (e != cudaSuccess && rc == DVBS2_OK) rc = fail_cuda(h, e, "cudaStreamSynchronize(pipe)");
+    }
+    return rc;
 }
 
 // transmitter state: tables + payload/codeword words for max_frames
@@ -725,6 +780,7 @@ extern "C"
     {
         if (!h) return DVBS2_ERR_INVALID;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         CU(h, cudaStreamSynchronize(h->stream));
         for (int i = 0; i < N_PIPE; i++)
             CU(h, cudaStreamSynchronize(h->pipe[i]));
@@ -740,6 +796,8 @@ extern "C"
         st->frames = v[STAT_FRAMES], st->ldpc_iterations = v[STAT_LDPC_ITERS], st->ldpc_failures = v[STAT_LDPC_FAIL];
         st->bch_nonzero = v[STAT_BCH_NONZERO], st->bch_failures = v[STAT_BCH_FAIL];
         st->kernel_launches = h->launches;
+        for (int i = 0; i < LDPC_HIST_BINS; i++)
+            st->iter_hist[i] = v[STAT_ITER_HIST + i];
         return DVBS2_OK;
     }
 
@@ -760,6 +818,7 @@ extern "C"
     {
         if (!h) return DVBS2_ERR_INVALID;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         if (!enable) TRY(prof_collect(h));
         h->profiling = enable != 0;
         return DVBS2_OK;
@@ -769,6 +828,7 @@ extern "C"
     {
         if (!h || !t) return DVBS2_ERR_INVALID;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         TRY(prof_collect(h));
         t->demap_ms = h->t_ms[P_DEMAP], t->ldpc_ms = h->t_ms[P_LDPC], t->bch_ms = h->t_ms[P_BCH];
         t->unpack_ms = h->t_ms[P_UNPACK], t->pack_ms = h->t_ms[P_PACK];
@@ -781,6 +841,7 @@ extern "C"
     {
         if (!h || !ptr) return DVBS2_ERR_INVALID;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         CU(h, cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
         return DVBS2_OK;
     }
@@ -799,8 +860,8 @@ extern "C"
         if (!d_CP || !d_Y_N1 || !d_Y_N2) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         CU(h, launch_demap_frames(demap_args(h, d_CP, d_Y_N1, n_frames), d_Y_N2, deinterleave, h->stream));
-        h->launches += 1;
         return DVBS2_OK;
     }
 
@@ -810,6 +871,7 @@ extern "C"
         TRY(check_frames(h, n_frames));
         if (!d_Y_N || !d_V_K) return DVBS2_ERR_INVALID;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         return run_ldpc(h, h->stream, 0, d_Y_N, d_CWD, d_V_K, d_n_iter, n_frames);
     }
 
@@ -819,6 +881,7 @@ extern "C"
         TRY(check_frames(h, n_frames));
         if (!d_Y_N || !d_V_K) return DVBS2_ERR_INVALID;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         return run_bch(h, h->stream, 0, d_Y_N, d_CWD, d_V_K, n_frames);
     }
 
@@ -828,6 +891,7 @@ extern "C"
         TRY(check_frames(h, n_frames));
         if (!d_CP || !d_Y_N1 || !d_V_K) return DVBS2_ERR_INVALID;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         return run_chain(h, h->stream, 0, d_CP, d_Y_N1, d_CWD_ldpc, d_CWD_bch, d_V_K, d_n_iter, n_frames);
     }
 
@@ -837,6 +901,7 @@ extern "C"
         TRY(check_frames(h, n_frames));
         if (!d_CP || !d_Y_N1 || !d_V_K_packed) return DVBS2_ERR_INVALID;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         return run_chain(h, h->stream, 0, d_CP, d_Y_N1, d_CWD_ldpc, d_CWD_bch, nullptr, d_n_iter, n_frames, d_V_K_packed,
                          descramble);
     }
@@ -848,6 +913,7 @@ extern "C"
         if (!CP || !Y_N1 || !Y_N2) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         const size_t symf = (size_t)2 * h->mc.n_sym * sizeof(float), llrf = (size_t)N_LDPC * sizeof(float);
         TRY(ensure(h, h->in_a, symf * n_frames));
         TRY(ensure(h, h->out_a, llrf * n_frames));
@@ -856,7 +922,6 @@ extern "C"
         CU(h, cudaMemcpyAsync(h->sigma.p, CP, sizeof(float) * n_frames, cudaMemcpyHostToDevice, s));
         CU(h, cudaMemcpyAsync(h->in_a.p, Y_N1, symf * n_frames, cudaMemcpyHostToDevice, s));
         CU(h, launch_demap_frames(demap_args(h, (float*)h->sigma.p, (float*)h->in_a.p, n_frames), (float*)h->out_a.p, 0, s));
-        h->launches += 1;
         CU(h, cudaMemcpyAsync(Y_N2, h->out_a.p, llrf * n_frames, cudaMemcpyDeviceToHost, s));
         CU(h, cudaStreamSynchronize(s));
         return DVBS2_OK;
@@ -868,6 +933,7 @@ extern "C"
         if (!itl || !nat) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         const size_t llrf = (size_t)N_LDPC * sizeof(float);
         TRY(ensure(h, h->in_a, llrf * n_frames));
         TRY(ensure(h, h->out_a, llrf * n_frames));
@@ -875,7 +941,6 @@ extern "C"
         CU(h, cudaMemcpyAsync(h->in_a.p, itl, llrf * n_frames, cudaMemcpyHostToDevice, s));
         CU(h, launch_deinterleave((float*)h->in_a.p, (float*)h->out_a.p, n_frames, h->mc.n_sym, h->mc.itl_cols,
                                   h->mc.itl_rev, s));
-        h->launches += 1;
         CU(h, cudaMemcpyAsync(nat, h->out_a.p, llrf * n_frames, cudaMemcpyDeviceToHost, s));
         CU(h, cudaStreamSynchronize(s));
         return DVBS2_OK;
@@ -886,12 +951,12 @@ extern "C"
         if (!h || !in || !out || h->cfg.precision == DVBS2_PREC_F32) return DVBS2_ERR_INVALID;
         if (n == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         TRY(ensure(h, h->in_a, n * sizeof(float)));
         TRY(ensure(h, h->out_a, n * h->elt));
         cudaStream_t s = h->stream;
         CU(h, cudaMemcpyAsync(h->in_a.p, in, n * sizeof(float), cudaMemcpyHostToDevice, s));
         CU(h, launch_quantize((float*)h->in_a.p, h->out_a.p, h->cfg.precision, n, h->cfg.quant_dec, h->cfg.quant_bits, s));
-        h->launches += 1;
         CU(h, cudaMemcpyAsync(out, h->out_a.p, n * h->elt, cudaMemcpyDeviceToHost, s));
         CU(h, cudaStreamSynchronize(s));
         return DVBS2_OK;
@@ -904,28 +969,29 @@ extern "C"
         if (!Y_N || !V_K) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         const size_t inf = (size_t)N_LDPC * h->elt, outf = (size_t)h->mc.N_bch * sizeof(int32_t);
         TRY(ensure(h, h->in_a, inf * n_frames));
         TRY(ensure(h, h->out_a, outf * n_frames));
         const int per = chunk_frames(h, n_frames);
-        int ci = 0;
-        for (int f0 = 0; f0 < n_frames; f0 += per, ci++)
-        {
-            const int nf = std::min(per, n_frames - f0);
-            cudaStream_t s = h->pipe[ci % N_PIPE];
-            char* d_in = (char*)h->in_a.p + inf * f0;
-            int32_t* d_out = (int32_t*)((char*)h->out_a.p + outf * f0);
-            int8_t* d_cwd = (int8_t*)h->cwd_ldpc.p + f0;
-            int32_t* d_nit = (int32_t*)h->nit.p + f0;
-            CU(h, cudaMemcpyAsync(d_in, (const char*)Y_N + inf * f0, inf * nf, cudaMemcpyHostToDevice, s));
-            TRY(run_ldpc(h, s, f0, d_in, d_cwd, d_out, d_nit, nf));
-            CU(h, cudaMemcpyAsync((char*)V_K + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
-            if (CWD) CU(h, cudaMemcpyAsync(CWD + f0, d_cwd, nf, cudaMemcpyDeviceToHost, s));
-            if (n_iter) CU(h, cudaMemcpyAsync(n_iter + f0, d_nit, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, s));
-        }
-        for (int i = 0; i < N_PIPE; i++)
-            CU(h, cudaStreamSynchronize(h->pipe[i]));
-        return DVBS2_OK;
+        int ci = 0, rc = DVBS2_OK;
+        for (int f0 = 0; f0 < n_frames && rc == DVBS2_OK; f0 += per, ci++)
+            rc = [&]() -> int {
+                const int nf = std::min(per, n_frames - f0);
+                cudaStream_t s = h->pipe[ci % N_PIPE];
+                char* d_in = (char*)h->in_a.p + inf * f0;
+                int32_t* d_out = (int32_t*)((char*)h->out_a.p + outf * f0);
+                int8_t* d_cwd = (int8_t*)h->cwd_ldpc.p + f0;
+                int32_t* d_nit = (int32_t*)h->nit.p + f0;
+                CU(h, cudaMemcpyAsync(d_in, (const char*)Y_N + inf * f0, inf * nf, cudaMemcpyHostToDevice, s));
+                TRY(run_ldpc(h, s, f0, d_in, d_cwd, d_out, d_nit, nf));
+                CU(h, cudaMemcpyAsync((char*)V_K + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
+                if (CWD) CU(h, cudaMemcpyAsync(CWD + f0, d_cwd, nf, cudaMemcpyDeviceToHost, s));
+                if (n_iter) CU(h, cudaMemcpyAsync(n_iter + f0, d_nit, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, s));
+                return DVBS2_OK;
+            }();
+        const int rs = sync_pipes(h); // also after a failure: nothing queued may outlive the call
+        return rc != DVBS2_OK ? rc : rs;
     }
 
     int dvbs2_cuda_bch_decode_hiho(dvbs2_cuda_handle* h, const int32_t* Y_N, int8_t* CWD, int32_t* V_K, int n_frames)
@@ -934,70 +1000,81 @@ extern "C"
         if (!Y_N || !V_K) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         const size_t inf = (size_t)h->mc.N_bch * sizeof(int32_t), outf = (size_t)h->mc.K_bch * sizeof(int32_t);
         TRY(ensure(h, h->in_a, inf * n_frames));
         TRY(ensure(h, h->out_a, outf * n_frames));
         const int per = chunk_frames(h, n_frames);
-        int ci = 0;
-        for (int f0 = 0; f0 < n_frames; f0 += per, ci++)
-        {
-            const int nf = std::min(per, n_frames - f0);
-            cudaStream_t s = h->pipe[ci % N_PIPE];
-            int32_t* d_in = (int32_t*)((char*)h->in_a.p + inf * f0);
-            int32_t* d_out = (int32_t*)((char*)h->out_a.p + outf * f0);
-            int8_t* d_cwd = (int8_t*)h->cwd_bch.p + f0;
-            CU(h, cudaMemcpyAsync(d_in, (const char*)Y_N + inf * f0, inf * nf, cudaMemcpyHostToDevice, s));
-            TRY(run_bch(h, s, f0, d_in, d_cwd, d_out, nf));
-            CU(h, cudaMemcpyAsync((char*)V_K + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
-            if (CWD) CU(h, cudaMemcpyAsync(CWD + f0, d_cwd, nf, cudaMemcpyDeviceToHost, s));
-        }
-        for (int i = 0; i < N_PIPE; i++)
-            CU(h, cudaStreamSynchronize(h->pipe[i]));
-        return DVBS2_OK;
+        int ci = 0, rc = DVBS2_OK;
+        for (int f0 = 0; f0 < n_frames && rc == DVBS2_OK; f0 += per, ci++)
+            rc = [&]() -> int {
+                const int nf = std::min(per, n_frames - f0);
+                cudaStream_t s = h->pipe[ci % N_PIPE];
+                int32_t* d_in = (int32_t*)((char*)h->in_a.p + inf * f0);
+                int32_t* d_out = (int32_t*)((char*)h->out_a.p + outf * f0);
+                int8_t* d_cwd = (int8_t*)h->cwd_bch.p + f0;
+                CU(h, cudaMemcpyAsync(d_in, (const char*)Y_N + inf * f0, inf * nf, cudaMemcpyHostToDevice, s));
+                TRY(run_bch(h, s, f0, d_in, d_cwd, d_out, nf));
+                CU(h, cudaMemcpyAsync((char*)V_K + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
+                if (CWD) CU(h, cudaMemcpyAsync(CWD + f0, d_cwd, nf, cudaMemcpyDeviceToHost, s));
+                return DVBS2_OK;
+            }();
+        const int rs = sync_pipes(h);
+        return rc != DVBS2_OK ? rc : rs;
     }
 
-    // V_K: int32 per bit (AFF3CT socket type) when packed == nullptr, else packed bytes
-    // pl_frames: Y_N1 holds whole PL frames (Framer::remove_plh fused in).  CP == nullptr: sigma comes from the on-device
-    // Estimator_DVBS2 and is returned in SIG (optional).
-    static int chain_host(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
+    // The fused stage on host buffers, chunked over the pipeline streams (H2D of chunk i+1 and D2H of chunk i-1 overlap the
+    // kernels of chunk i).  Input: symbols in any dvbs2_iq_format (XFEC or whole PL frames; CP == nullptr: sigma from the
+    // on-device Estimator_DVBS2, returned in SIG), or — llr8 — int8 LLRs for the int16 decoder.  Output: int32 per bit
+    // (AFF3CT socket type) when packed == nullptr, else packed bytes.
+    static int chain_host(dvbs2_cuda_handle* h, const float* CP, const void* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
                           int32_t* V_K, uint8_t* packed, int descramble, int32_t* n_iter, int n_frames, bool pl_frames = false,
-                          float* SIG = nullptr)
+                          float* SIG = nullptr, int iq_fmt = DVBS2_IQ_F32, float iq_scale = 1.f, bool llr8 = false)
     {
         TRY(check_frames(h, n_frames));
-        if (!Y_N1 || (!V_K && !packed)) return DVBS2_ERR_INVALID;
+        if (!Y_N1 || (V_K != nullptr) == (packed != nullptr)) return DVBS2_ERR_INVALID; // exactly one output format
+        if (iq_fmt < DVBS2_IQ_F32 || iq_fmt > DVBS2_IQ_SC8 || !(iq_scale > 0.f)) return DVBS2_ERR_INVALID;
+        if (llr8 && h->cfg.precision != DVBS2_PREC_I16) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
-        const size_t inf = (size_t)2 * (pl_frames ? pl_frame_symbols(h->mc.n_sym) : h->mc.n_sym) * sizeof(float);
+        LaunchScope launch_scope(h);
+        const size_t inf = llr8 ? (size_t)N_LDPC
+                                : (size_t)2 * (pl_frames ? pl_frame_symbols(h->mc.n_sym) : h->mc.n_sym) * iq_format_bytes(iq_fmt);
         const size_t outf = packed ? (size_t)h->mc.K_bch / 8 : (size_t)h->mc.K_bch * sizeof(int32_t);
         TRY(ensure(h, h->in_a, inf * n_frames));
         TRY(ensure(h, h->out_a, outf * n_frames));
         TRY(ensure(h, h->sigma, sizeof(float) * n_frames));
         const int per = chunk_frames(h, n_frames);
         char* const host_out = packed ? (char*)packed : (char*)V_K;
-        int ci = 0;
-        for (int f0 = 0; f0 < n_frames; f0 += per, ci++)
-        {
-            const int nf = std::min(per, n_frames - f0);
-            cudaStream_t s = h->pipe[ci % N_PIPE];
-            float* d_sym = (float*)((char*)h->in_a.p + inf * f0);
-            float* d_sig = (float*)h->sigma.p + f0;
-            char* d_out = (char*)h->out_a.p + outf * f0;
-            int8_t* d_c1 = (int8_t*)h->cwd_ldpc.p + f0;
-            int8_t* d_c2 = (int8_t*)h->cwd_bch.p + f0;
-            int32_t* d_nit = (int32_t*)h->nit.p + f0;
-            if (CP) CU(h, cudaMemcpyAsync(d_sig, CP + f0, sizeof(float) * nf, cudaMemcpyHostToDevice, s));
-            CU(h, cudaMemcpyAsync(d_sym, (const char*)Y_N1 + inf * f0, inf * nf, cudaMemcpyHostToDevice, s));
-            TRY(run_chain(h, s, f0, d_sig, d_sym, d_c1, d_c2, packed ? nullptr : (int32_t*)d_out, d_nit, nf,
-                          packed ? (uint8_t*)d_out : nullptr, descramble, pl_frames, CP ? nullptr : d_sig));
-            if (SIG) CU(h, cudaMemcpyAsync(SIG + f0, d_sig, sizeof(float) * nf, cudaMemcpyDeviceToHost, s));
-            CU(h, cudaMemcpyAsync(host_out + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
-            if (CWD_ldpc) CU(h, cudaMemcpyAsync(CWD_ldpc + f0, d_c1, nf, cudaMemcpyDeviceToHost, s));
-            if (CWD_bch) CU(h, cudaMemcpyAsync(CWD_bch + f0, d_c2, nf, cudaMemcpyDeviceToHost, s));
-            if (n_iter) CU(h, cudaMemcpyAsync(n_iter + f0, d_nit, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, s));
-        }
-        for (int i = 0; i < N_PIPE; i++)
-            CU(h, cudaStreamSynchronize(h->pipe[i]));
-        return DVBS2_OK;
+        int ci = 0, rc = DVBS2_OK;
+        for (int f0 = 0; f0 < n_frames && rc == DVBS2_OK; f0 += per, ci++)
+            rc = [&]() -> int {
+                const int nf = std::min(per, n_frames - f0);
+                cudaStream_t s = h->pipe[ci % N_PIPE];
+                char* d_in = (char*)h->in_a.p + inf * f0;
+                float* d_sig = (float*)h->sigma.p + f0;
+                char* d_out = (char*)h->out_a.p + outf * f0;
+                int8_t* d_c1 = (int8_t*)h->cwd_ldpc.p + f0;
+                int8_t* d_c2 = (int8_t*)h->cwd_bch.p + f0;
+                int32_t* d_nit = (int32_t*)h->nit.p + f0;
+                if (CP) CU(h, cudaMemcpyAsync(d_sig, CP + f0, sizeof(float) * nf, cudaMemcpyHostToDevice, s));
+                CU(h, cudaMemcpyAsync(d_in, (const char*)Y_N1 + inf * f0, inf * nf, cudaMemcpyHostToDevice, s));
+                if (llr8)
+                    TRY(run_llr8_chain(h, s, f0, (const int8_t*)d_in, d_c1, d_c2, packed ? nullptr : (int32_t*)d_out,
+                                       packed ? (uint8_t*)d_out : nullptr, descramble, d_nit, nf));
+                else
+                    TRY(run_chain(h, s, f0, d_sig, (const float*)d_in, d_c1, d_c2, packed ? nullptr : (int32_t*)d_out, d_nit, nf,
+                                  packed ? (uint8_t*)d_out : nullptr, descramble, pl_frames, CP ? nullptr : d_sig, iq_fmt,
+                                  iq_scale));
+                if (SIG) CU(h, cudaMemcpyAsync(SIG + f0, d_sig, sizeof(float) * nf, cudaMemcpyDeviceToHost, s));
+                CU(h, cudaMemcpyAsync(host_out + outf * f0, d_out, outf * nf, cudaMemcpyDeviceToHost, s));
+                if (CWD_ldpc) CU(h, cudaMemcpyAsync(CWD_ldpc + f0, d_c1, nf, cudaMemcpyDeviceToHost, s));
+                if (CWD_bch) CU(h, cudaMemcpyAsync(CWD_bch + f0, d_c2, nf, cudaMemcpyDeviceToHost, s));
+                if (n_iter) CU(h, cudaMemcpyAsync(n_iter + f0, d_nit, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, s));
+                return DVBS2_OK;
+            }();
+        const int rs = sync_pipes(h); // also after a failure: nothing queued may outlive the call
+        return rc != DVBS2_OK ? rc : rs;
     }
 
     int dvbs2_cuda_chain(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
@@ -1014,6 +1091,50 @@ extern "C"
         return chain_host(h, CP, Y_N1, CWD_ldpc, CWD_bch, nullptr, V_K_packed, descramble, n_iter, n_frames);
     }
 
+    // -------------------------------------------------------- compact socket formats
+    size_t dvbs2_cuda_iq_frame_bytes(const dvbs2_cuda_handle* h, int iq_format, int pl_frames)
+    {
+        if (!h || iq_format < DVBS2_IQ_F32 || iq_format > DVBS2_IQ_SC8) return 0;
+        return (size_t)2 * (pl_frames ? pl_frame_symbols(h->mc.n_sym) : h->mc.n_sym) * iq_format_bytes(iq_format);
+    }
+
+    int dvbs2_cuda_chain_compact(dvbs2_cuda_handle* h, int iq_format, float iq_scale, const float* CP, const void* Y_N1,
+                                 float* SIG, int8_t* CWD_ldpc, int8_t* CWD_bch, int32_t* V_K, uint8_t* V_K_packed,
+                                 int descramble, int32_t* n_iter, int pl_frames, int n_frames)
+    {
+        if (!CP && !pl_frames) return DVBS2_ERR_INVALID; // the estimator works on PL frames' payload; XFEC callers pass sigma
+        return chain_host(h, CP, Y_N1, CWD_ldpc, CWD_bch, V_K, V_K_packed, descramble, n_iter, n_frames, pl_frames != 0, SIG,
+                          iq_format, iq_scale);
+    }
+
+    int dvbs2_cuda_chain_compact_dev(dvbs2_cuda_handle* h, int iq_format, float iq_scale, const float* d_CP,
+                                     const void* d_Y_N1, float* d_SIG, int8_t* d_CWD_ldpc, int8_t* d_CWD_bch, int32_t* d_V_K,
+                                     uint8_t* d_V_K_packed, int descramble, int32_t* d_n_iter, int pl_frames, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!d_Y_N1 || (d_V_K != nullptr) == (d_V_K_packed != nullptr) || (!d_CP && (!d_SIG || !pl_frames))) return DVBS2_ERR_INVALID;
+        if (iq_format < DVBS2_IQ_F32 || iq_format > DVBS2_IQ_SC8 || !(iq_scale > 0.f)) return DVBS2_ERR_INVALID;
+        CU(h, cudaSetDevice(h->cfg.device));
+        return run_chain(h, h->stream, 0, d_CP, (const float*)d_Y_N1, d_CWD_ldpc, d_CWD_bch, d_V_K, d_n_iter, n_frames,
+                         d_V_K_packed, descramble, pl_frames != 0, d_CP ? nullptr : d_SIG, iq_format, iq_scale);
+    }
+
+    int dvbs2_cuda_decode_llr8(dvbs2_cuda_handle* h, const int8_t* Y_N, int8_t* CWD_ldpc, int8_t* CWD_bch, int32_t* V_K,
+                               uint8_t* V_K_packed, int descramble, int32_t* n_iter, int n_frames)
+    {
+        return chain_host(h, nullptr, Y_N, CWD_ldpc, CWD_bch, V_K, V_K_packed, descramble, n_iter, n_frames, false, nullptr,
+                          DVBS2_IQ_F32, 1.f, true);
+    }
+
+    int dvbs2_cuda_decode_llr8_dev(dvbs2_cuda_handle* h, const int8_t* d_Y_N, int8_t* d_CWD_ldpc, int8_t* d_CWD_bch,
+                                   int32_t* d_V_K, uint8_t* d_V_K_packed, int descramble, int32_t* d_n_iter, int n_frames)
+    {
+        TRY(check_frames(h, n_frames));
+        if (!d_Y_N || (d_V_K != nullptr) == (d_V_K_packed != nullptr) || h->cfg.precision != DVBS2_PREC_I16) return DVBS2_ERR_INVALID;
+        CU(h, cudaSetDevice(h->cfg.device));
+        return run_llr8_chain(h, h->stream, 0, d_Y_N, d_CWD_ldpc, d_CWD_bch, d_V_K, d_V_K_packed, descramble, d_n_iter, n_frames);
+    }
+
     // -------------------------------------------------------- receiver stage from PL frames
     int dvbs2_cuda_pl_frame_size(const dvbs2_cuda_handle* h)
     {
@@ -1026,13 +1147,13 @@ extern "C"
         if (!Y_N1 || !Y_N2) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         const size_t inf = (size_t)2 * pl_frame_symbols(h->mc.n_sym) * sizeof(float), outf = (size_t)2 * h->mc.n_sym * sizeof(float);
         TRY(ensure(h, h->in_a, inf * n_frames));
         TRY(ensure(h, h->out_a, outf * n_frames));
         cudaStream_t s = h->stream;
         CU(h, cudaMemcpyAsync(h->in_a.p, Y_N1, inf * n_frames, cudaMemcpyHostToDevice, s));
         CU(h, launch_remove_plh((const float*)h->in_a.p, (float*)h->out_a.p, h->mc.n_sym, n_frames, s));
-        h->launches += 1;
         CU(h, cudaMemcpyAsync(Y_N2, h->out_a.p, outf * n_frames, cudaMemcpyDeviceToHost, s));
         CU(h, cudaStreamSynchronize(s));
         return DVBS2_OK;
@@ -1044,8 +1165,8 @@ extern "C"
         if (!d_Y_N1 || !d_Y_N2) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         CU(h, launch_remove_plh(d_Y_N1, d_Y_N2, h->mc.n_sym, n_frames, h->stream));
-        h->launches += 1;
         return DVBS2_OK;
     }
 
@@ -1055,6 +1176,7 @@ extern "C"
         if (!X_N || !SIG) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         const size_t inf = (size_t)2 * h->mc.n_sym * sizeof(float);
         TRY(ensure(h, h->in_a, inf * n_frames));
         TRY(ensure(h, h->out_a, 3 * sizeof(float) * (size_t)n_frames));
@@ -1063,7 +1185,6 @@ extern "C"
         float *d_eb = d_sig + n_frames, *d_es = d_sig + 2 * (size_t)n_frames;
         CU(h, cudaMemcpyAsync(h->in_a.p, X_N, inf * n_frames, cudaMemcpyHostToDevice, s));
         CU(h, launch_estimate(demap_args(h, nullptr, (const float*)h->in_a.p, n_frames), h->mc.K_bch, d_sig, d_eb, d_es, s));
-        h->launches += 1;
         CU(h, cudaMemcpyAsync(SIG, d_sig, sizeof(float) * n_frames, cudaMemcpyDeviceToHost, s));
         if (Eb_N0) CU(h, cudaMemcpyAsync(Eb_N0, d_eb, sizeof(float) * n_frames, cudaMemcpyDeviceToHost, s));
         if (Es_N0) CU(h, cudaMemcpyAsync(Es_N0, d_es, sizeof(float) * n_frames, cudaMemcpyDeviceToHost, s));
@@ -1078,15 +1199,14 @@ extern "C"
         if (!d_X_N || !d_SIG) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         CU(h, launch_estimate(demap_args(h, nullptr, d_X_N, n_frames), h->mc.K_bch, d_SIG, d_Eb_N0, d_Es_N0, h->stream));
-        h->launches += 1;
         return DVBS2_OK;
     }
 
     int dvbs2_cuda_rx_chain(dvbs2_cuda_handle* h, const float* PL_frames, const float* CP, float* SIG, int8_t* CWD_ldpc,
                             int8_t* CWD_bch, int32_t* V_K, uint8_t* V_K_packed, int descramble, int32_t* n_iter, int n_frames)
     {
-        if ((V_K != nullptr) == (V_K_packed != nullptr)) return DVBS2_ERR_INVALID; // exactly one output format
         return chain_host(h, CP, PL_frames, CWD_ldpc, CWD_bch, V_K, V_K_packed, descramble, n_iter, n_frames, true, SIG);
     }
 
@@ -1097,6 +1217,7 @@ extern "C"
         TRY(check_frames(h, n_frames));
         if (!d_PL_frames || (d_V_K != nullptr) == (d_V_K_packed != nullptr) || (!d_CP && !d_SIG)) return DVBS2_ERR_INVALID;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         return run_chain(h, h->stream, 0, d_CP, d_PL_frames, d_CWD_ldpc, d_CWD_bch, d_V_K, d_n_iter, n_frames, d_V_K_packed,
                          descramble, true, d_CP ? nullptr : d_SIG);
     }
@@ -1108,13 +1229,13 @@ extern "C"
         if (!U) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         TRY(tx_init(h));
         const size_t bytes = (size_t)n_frames * h->mc.K_bch * sizeof(int32_t);
         TRY(ensure(h, h->in_a, bytes));
         cudaStream_t s = h->stream;
         CU(h, cudaMemcpyAsync(h->in_a.p, U, bytes, cudaMemcpyHostToDevice, s));
         CU(h, launch_pack_bits((const int32_t*)h->in_a.p, (uint32_t*)h->tx_src.p, h->mc.K_bch, h->mc.K_bch, n_frames, s));
-        h->launches += 1;
         h->tx_encoded_groups = 0;
         CU(h, cudaStreamSynchronize(s));
         return DVBS2_OK;
@@ -1125,9 +1246,9 @@ extern "C"
         TRY(check_frames(h, n_frames));
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         TRY(tx_init(h));
         CU(h, launch_tx_random_payload((uint32_t*)h->tx_src.p, h->mc.K_bch, (n_frames + 31) / 32, seed, h->stream));
-        h->launches += 1;
         h->tx_encoded_groups = 0;
         return DVBS2_OK;
     }
@@ -1139,16 +1260,15 @@ extern "C"
         if (!d_CP || !d_Y_N1 || !(sigma >= 0.f) || !h->tx_src.p) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         const TxLaunch t = tx_args(h, n_frames);
         if (h->tx_encoded_groups < t.n_groups)
         { // a later call may ask for more frames of the same payload than the one that triggered the encoder
             CU(h, launch_tx_encode(t, h->stream));
-            h->launches += 2;
             h->tx_encoded_groups = t.n_groups;
         }
         CU(h, launch_tx_modulate_awgn(t, h->d_cstl, d_Y_N1, d_CP, h->mc.bps, h->mc.n_sym, h->mc.itl_cols, h->mc.itl_rev,
                                       sigma, seed, h->stream));
-        h->launches += 1;
         return DVBS2_OK;
     }
 
@@ -1158,10 +1278,10 @@ extern "C"
         if (!out || stage < 0 || stage > 3 || !h->tx_src.p) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         if (stage > 0 && h->tx_encoded_groups < (n_frames + 31) / 32)
         {
             CU(h, launch_tx_encode(tx_args(h, n_frames), h->stream));
-            h->launches += 2;
             h->tx_encoded_groups = (n_frames + 31) / 32;
         }
         const int len = stage <= 1 ? h->mc.K_bch : stage == 2 ? h->mc.N_bch : N_LDPC;
@@ -1170,7 +1290,6 @@ extern "C"
         const size_t bytes = (size_t)n_frames * len * sizeof(int32_t);
         TRY(ensure(h, h->out_a, bytes));
         CU(h, launch_unpack_bits(words, (int32_t*)h->out_a.p, stride, len, n_frames, h->stream));
-        h->launches += 1;
         CU(h, cudaMemcpyAsync(out, h->out_a.p, bytes, cudaMemcpyDeviceToHost, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
         return DVBS2_OK;
@@ -1182,9 +1301,9 @@ extern "C"
         if (!h->tx_src.p) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
+        LaunchScope launch_scope(h);
         CU(h, launch_monitor((const uint32_t*)h->out_hd.p, N_LDPC, tx_args(h, n_frames), (unsigned long long*)h->mon.p,
                              h->stream));
-        h->launches += 1;
         return DVBS2_OK;
     }
 

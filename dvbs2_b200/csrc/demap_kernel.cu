@@ -13,6 +13,7 @@
 // Both are pure streaming kernels (HBM-bound: 8 B/symbol in, 4 B/LLR out).
 #include <cmath>
 #include <cstdint>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "kernels.h"
@@ -29,6 +30,22 @@ __device__ __forceinline__ float
 max_star(float a, float b)
 {
     return fmaxf(a, b) + __logf(1.0f + __expf(-fabsf(a - b)));
+}
+
+// Component i of the symbol buffer in its wire format (compact input sockets).  The integer formats are
+// converted exactly as a host-side adaptor would before handing floats to Modem::demodulate — (float)x * scale, one rounded
+// multiply that is never fused into the distance computation — so transporting sc16 / sc8 / half instead of float changes
+// no bit of the result for the same sample values.
+__device__ __forceinline__ float
+load_sym(const DemapLaunch& a, size_t i)
+{
+    switch (a.sym_fmt)
+    {
+        case 1: return __half2float(__ldg(reinterpret_cast<const __half*>(a.sym) + i));
+        case 2: return __fmul_rn((float)__ldg(reinterpret_cast<const int16_t*>(a.sym) + i), a.iq_scale);
+        case 3: return __fmul_rn((float)__ldg(reinterpret_cast<const int8_t*>(a.sym) + i), a.iq_scale);
+        default: return __ldg(a.sym + i);
+    }
 }
 
 // LLRs of one received symbol: out[b], b = 0..BPS-1
@@ -102,8 +119,8 @@ demap_frames_kernel(const DemapLaunch a, float* __restrict__ llr, int deinterlea
     if (k >= a.n_sym) return;
     const float sg = a.sigma[f];
     const float inv = 1.0f / (2 * sg * sg);
-    const float2 y = a.pl_sym > 0 ? reinterpret_cast<const float2*>(a.sym + (size_t)f * 2 * a.pl_sym)[pl_symbol_pos(k, a.n_sym)]
-                                  : reinterpret_cast<const float2*>(a.sym + (size_t)f * 2 * a.n_sym)[k];
+    const size_t at = a.pl_sym > 0 ? (size_t)f * 2 * a.pl_sym + 2 * pl_symbol_pos(k, a.n_sym) : (size_t)f * 2 * a.n_sym + 2 * k;
+    const float2 y = make_float2(load_sym(a, at), load_sym(a, at + 1));
     float out[BPS];
     demap_symbol<BPS>(y.x, y.y, inv, cs, out);
     float* o = llr + (size_t)f * N_LDPC;
@@ -183,7 +200,7 @@ __global__ void __launch_bounds__(DemapCfg<NF>::WARPS * 32) demap_to_var_kernel(
         {
             const int r = r0 + sub;
             const int f = (g * NF + j) * 32 + r;
-            tile[warp][j][r][col] = (f < a.n_frames && in_frame) ? __ldg(a.sym + (size_t)f * nfl + e) : 0.f;
+            tile[warp][j][r][col] = (f < a.n_frames && in_frame) ? load_sym(a, (size_t)f * nfl + e) : 0.f;
         }
     __syncwarp();
     float inv[NF];
@@ -256,7 +273,7 @@ __global__ void __launch_bounds__(128) estimate_kernel(const DemapLaunch a, int 
         for (int r = 0; r < 32; r++)
         {
             const int f = sg * 32 + r;
-            tile[warp][buf][r][lane] = (f < a.n_frames && in_frame) ? __ldg(a.sym + (size_t)f * nfl + e) : 0.f;
+            tile[warp][buf][r][lane] = (f < a.n_frames && in_frame) ? load_sym(a, (size_t)f * nfl + e) : 0.f;
         }
     };
     float m2 = 0.f, m4 = 0.f;
@@ -313,9 +330,9 @@ launch_demap_frames(const DemapLaunch& a, float* llr, int deinterleave, cudaStre
     const dim3 grid(a.n_frames, (a.n_sym + 255) / 256);
     switch (a.bps)
     {
-        case 2: demap_frames_kernel<2><<<grid, 256, 0, s>>>(a, llr, deinterleave); break;
-        case 3: demap_frames_kernel<3><<<grid, 256, 0, s>>>(a, llr, deinterleave); break;
-        case 4: demap_frames_kernel<4><<<grid, 256, 0, s>>>(a, llr, deinterleave); break;
+        case 2: demap_frames_kernel<2><<<grid, 256, 0, s>>>(a, llr, deinterleave); count_launch(); break;
+        case 3: demap_frames_kernel<3><<<grid, 256, 0, s>>>(a, llr, deinterleave); count_launch(); break;
+        case 4: demap_frames_kernel<4><<<grid, 256, 0, s>>>(a, llr, deinterleave); count_launch(); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -328,7 +345,7 @@ demap_to_var_launch(const DemapLaunch& a, void* var, cudaStream_t s)
     constexpr int WARPS = DemapCfg<NF>::WARPS;
     const int groups = (a.n_frames + 32 * NF - 1) / (32 * NF); // whole decoder groups: pad frames get zeros
     const dim3 grid((a.n_sym + DemapCfg<NF>::SYMS * WARPS - 1) / (DemapCfg<NF>::SYMS * WARPS), groups);
-    demap_to_var_kernel<BPS, R, NF><<<grid, WARPS * 32, 0, s>>>(a, (R*)var);
+    demap_to_var_kernel<BPS, R, NF><<<grid, WARPS * 32, 0, s>>>(a, (R*)var); count_launch();
 }
 
 template<int BPS>
@@ -368,7 +385,7 @@ cudaError_t
 launch_remove_plh(const float* pl, float* out, int n_sym, int n_frames, cudaStream_t s)
 {
     const dim3 grid(n_frames, (n_sym + 255) / 256);
-    remove_plh_kernel<<<grid, 256, 0, s>>>((const float2*)pl, (float2*)out, n_sym, pl_frame_symbols(n_sym));
+    remove_plh_kernel<<<grid, 256, 0, s>>>((const float2*)pl, (float2*)out, n_sym, pl_frame_symbols(n_sym)); count_launch();
     return cudaGetLastError();
 }
 
@@ -376,7 +393,7 @@ cudaError_t
 launch_estimate(const DemapLaunch& a, int K_bch, float* sigma, float* ebn0, float* esn0, cudaStream_t s)
 {
     const int subgroups = (a.n_frames + 31) / 32;
-    estimate_kernel<<<(subgroups + 3) / 4, 128, 0, s>>>(a, K_bch, sigma, ebn0, esn0);
+    estimate_kernel<<<(subgroups + 3) / 4, 128, 0, s>>>(a, K_bch, sigma, ebn0, esn0); count_launch();
     return cudaGetLastError();
 }
 
@@ -385,7 +402,7 @@ launch_deinterleave(const float* itl, float* nat, int n_frames, int n_sym, int i
 {
     const int bps = N_LDPC / n_sym;
     const dim3 grid(n_frames, (N_LDPC + 255) / 256);
-    deinterleave_kernel<<<grid, 256, 0, s>>>(itl, nat, bps, n_sym, itl_cols, itl_rev);
+    deinterleave_kernel<<<grid, 256, 0, s>>>(itl, nat, bps, n_sym, itl_cols, itl_rev); count_launch();
     return cudaGetLastError();
 }
 
@@ -400,6 +417,7 @@ launch_quantize(const float* in, void* out, int precision, size_t n, int dec, in
         quantize_kernel<int8_t><<<blocks, 256, 0, s>>>(in, (int8_t*)out, n, factor, vmax);
     else
         return cudaErrorInvalidValue;
+    count_launch();
     return cudaGetLastError();
 }
 } // namespace dvbs2

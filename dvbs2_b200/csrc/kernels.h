@@ -9,6 +9,15 @@ namespace dvbs2
 {
 constexpr int LDPC_WARPS = 12; // warps of the persistent LDPC CTA (one CTA per SM)
 
+// Every kernel launch of the library is counted at its <<<>>> site (dvbs2_cuda_stats::kernel_launches).  The counter is
+// per host thread — a handle is driven by one thread at a time — and capi.cu credits the difference to the handle in use.
+uint64_t& launch_counter();
+inline void
+count_launch()
+{
+    launch_counter()++;
+}
+
 enum StatSlot
 {
     STAT_FRAMES = 0,
@@ -16,8 +25,10 @@ enum StatSlot
     STAT_LDPC_FAIL,
     STAT_BCH_NONZERO,
     STAT_BCH_FAIL,
-    STAT_COUNT
+    STAT_ITER_HIST,                       // [LDPC_HIST_BINS] frames that stopped after 0, 1, 2, ... iterations (last bin: >= 32)
+    STAT_COUNT = STAT_ITER_HIST + 33
 };
+constexpr int LDPC_HIST_BINS = 33;
 
 // Device-resident layout shared by the kernels.  "subgroup" = 32 consecutive frames (bit f of a bit-sliced word =
 // frame 32*subgroup + f); "group" = NF consecutive subgroups decoded by one warp, NF = ldpc_frames_per_lane(precision):
@@ -98,6 +109,8 @@ cudaError_t launch_ldpc_decode_coop(const LdpcLaunch& a, cudaStream_t s);
 // smallest distance (in checks) between two checks sharing an information variable that the cooperative kernel tolerates
 int ldpc_coop_min_reuse();
 cudaError_t launch_pack_llr(const void* in, void* var, int precision, int n_frames, int nf, cudaStream_t s);
+// int8 LLRs on the wire (compact input socket of the fixed-point decoder) into the int16 decoder's var layout
+cudaError_t launch_pack_llr8_as_i16(const int8_t* in, void* var, int n_frames, int nf, cudaStream_t s);
 // scr (optional): BB scrambler sequence, 8 bits per byte LSB first, XORed into the output (Scrambler_BB::descramble)
 cudaError_t launch_unpack_bits(const uint32_t* words, int32_t* out, int stride, int K, int n_frames, cudaStream_t s,
                                const uint8_t* scr = nullptr);
@@ -116,7 +129,15 @@ struct DemapLaunch
     int quant_dec, quant_bits; // for integer outputs
     int pl_sym;                // > 0: sym holds whole PL frames [frames][2*pl_sym]; the payload symbols are picked out in place
                                // (Framer::remove_plh fused into the read side), 0: sym holds XFEC frames
+    int sym_fmt;               // wire format of sym (dvbs2_iq_format): 0 float, 1 IEEE half, 2 int16 * iq_scale, 3 int8 * iq_scale
+    float iq_scale;            // value of one LSB for the integer formats
 };
+// bytes per I or Q component of a dvbs2_iq_format
+__host__ __device__ inline int
+iq_format_bytes(int fmt)
+{
+    return fmt == 0 ? 4 : fmt == 3 ? 1 : 2;
+}
 // PL frame geometry (src/common/Module/Framer/Framer.hxx:36-38,330-343; src/common/Factory/DVBS2/DVBS2.cpp:352-355): 90-symbol
 // header, then the payload with a 36-symbol pilot block after every 1440 payload symbols (n_sym / 1440 blocks in all)
 __host__ __device__ inline int

@@ -670,6 +670,7 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
                 const bool ok = !a.early_stop || !((failed[j] >> lane) & 1);
                 if (a.cwd) a.cwd[frame] = (int8_t)ok;
                 if (a.n_iter) a.n_iter[frame] = my_iters[j];
+                if (a.stats) atomicAdd(a.stats + STAT_ITER_HIST + min(my_iters[j], LDPC_HIST_BINS - 1), 1ull);
             }
             it_sum += __reduce_add_sync(FULL, fin ? my_iters[j] : 0);
             n_valid += __popc(done[j]);
@@ -975,6 +976,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
                 const bool ok = !a.early_stop || !((failed >> lane) & 1);
                 if (a.cwd) a.cwd[slot] = (int8_t)ok;
                 if (a.n_iter) a.n_iter[slot] = my_iters;
+                if (a.stats) atomicAdd(a.stats + STAT_ITER_HIST + min(my_iters, LDPC_HIST_BINS - 1), 1ull);
             }
             const int it_sum = __reduce_add_sync(FULL, fin ? my_iters : 0);
             if (lane == 0 && a.stats)
@@ -1179,9 +1181,9 @@ __global__ void __launch_bounds__(128) merge_back_kernel(const MergeLaunch c)
 // ---------------------------------------------------------------------------------------------- layout kernels
 // frame-major LLRs [F][16200] -> var[group][v][lane][NF] (frame = (group*NF + j)*32 + lane); frames past n_frames = 0.
 // One block per (32 variables, 32-frame subgroup).
-template<typename R>
+template<typename R, typename RI = R> // RI: element type on the wire (int8 LLRs feeding the int16 decoder)
 __global__ void
-pack_llr_kernel(const R* __restrict__ in, R* __restrict__ var, int n_frames, int nf)
+pack_llr_kernel(const RI* __restrict__ in, R* __restrict__ var, int n_frames, int nf)
 {
     __shared__ R tile[32][33];
     const int sg = blockIdx.y, v0 = blockIdx.x * 32; // sg = 32-frame subgroup index = group*nf + j
@@ -1190,7 +1192,7 @@ pack_llr_kernel(const R* __restrict__ in, R* __restrict__ var, int n_frames, int
     for (int k = y; k < 32; k += blockDim.y)
     {
         const int f = sg * 32 + k, v = v0 + x;
-        tile[k][x] = (f < n_frames && v < N_LDPC) ? in[(size_t)f * N_LDPC + v] : (R)0;
+        tile[k][x] = (f < n_frames && v < N_LDPC) ? (R)in[(size_t)f * N_LDPC + v] : (R)0;
     }
     __syncthreads();
     for (int k = y; k < 32; k += blockDim.y)
@@ -1290,7 +1292,7 @@ launch_ldpc_k(const LdpcLaunch& a, cudaStream_t s)
     // ... and a CTA carries only the warps it can feed, so that launches of other streams (pipeline chunks, other module
     // clones) fit beside it on the SM instead of waiting for a mostly idle 12-warp CTA to drain
     const int warps = std::min(LDPC_WARPS, std::max(1, (groups + blocks - 1) / std::max(1, blocks)));
-    k<<<blocks, warps * 32, smem, s>>>(a);
+    k<<<blocks, warps * 32, smem, s>>>(a); count_launch();
     return cudaGetLastError();
 }
 
@@ -1314,7 +1316,7 @@ launch_ldpc_coop_k(const LdpcLaunch& a, cudaStream_t s)
     e = cudaMemsetAsync(a.queue, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
     const int groups = (a.n_frames + 31) / 32;
-    k<<<groups < a.n_sms ? groups : a.n_sms, COOP_WARPS * 32, smem, s>>>(a);
+    k<<<groups < a.n_sms ? groups : a.n_sms, COOP_WARPS * 32, smem, s>>>(a); count_launch();
     return cudaGetLastError();
 }
 
@@ -1349,10 +1351,10 @@ template<typename R, int NF, int ND>
 static cudaError_t
 launch_compact_t(const CompactLaunch& c, cudaStream_t s)
 {
-    compact_scan_kernel<<<1, 1024, 0, s>>>(c);
-    compact_expand_kernel<<<(c.n_groups * c.nf + 127) / 128, 128, 0, s>>>(c);
+    compact_scan_kernel<<<1, 1024, 0, s>>>(c); count_launch();
+    compact_expand_kernel<<<(c.n_groups * c.nf + 127) / 128, 128, 0, s>>>(c); count_launch();
     const dim3 grid(c.cap / (32 * ND), (COMPACT_PARTS + 3) / 4);
-    if (grid.x > 0) compact_copy_kernel<R, NF, ND><<<grid, 128, 0, s>>>(c);
+    if (grid.x > 0) { compact_copy_kernel<R, NF, ND><<<grid, 128, 0, s>>>(c); count_launch(); }
     return cudaGetLastError();
 }
 
@@ -1393,7 +1395,7 @@ cudaError_t
 launch_merge_back(const MergeLaunch& c, cudaStream_t s)
 {
     const dim3 grid(c.n_groups, (COMPACT_PARTS + 3) / 4);
-    merge_back_kernel<<<grid, 128, 0, s>>>(c);
+    merge_back_kernel<<<grid, 128, 0, s>>>(c); count_launch();
     return cudaGetLastError();
 }
 
@@ -1404,11 +1406,20 @@ launch_pack_llr(const void* in, void* var, int precision, int n_frames, int nf, 
     const dim3 grid((N_LDPC + 31) / 32, groups * nf), block(32, 8);
     switch (precision)
     {
-        case 0: pack_llr_kernel<float><<<grid, block, 0, s>>>((const float*)in, (float*)var, n_frames, nf); break;
-        case 1: pack_llr_kernel<int16_t><<<grid, block, 0, s>>>((const int16_t*)in, (int16_t*)var, n_frames, nf); break;
-        case 2: pack_llr_kernel<int8_t><<<grid, block, 0, s>>>((const int8_t*)in, (int8_t*)var, n_frames, nf); break;
+        case 0: pack_llr_kernel<float><<<grid, block, 0, s>>>((const float*)in, (float*)var, n_frames, nf); count_launch(); break;
+        case 1: pack_llr_kernel<int16_t><<<grid, block, 0, s>>>((const int16_t*)in, (int16_t*)var, n_frames, nf); count_launch(); break;
+        case 2: pack_llr_kernel<int8_t><<<grid, block, 0, s>>>((const int8_t*)in, (int8_t*)var, n_frames, nf); count_launch(); break;
         default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t
+launch_pack_llr8_as_i16(const int8_t* in, void* var, int n_frames, int nf, cudaStream_t s)
+{
+    const int groups = (n_frames + 32 * nf - 1) / (32 * nf);
+    const dim3 grid((N_LDPC + 31) / 32, groups * nf), block(32, 8);
+    pack_llr_kernel<int16_t, int8_t><<<grid, block, 0, s>>>(in, (int16_t*)var, n_frames, nf); count_launch();
     return cudaGetLastError();
 }
 
@@ -1417,7 +1428,7 @@ launch_unpack_bits(const uint32_t* words, int32_t* out, int stride, int K, int n
 {
     const int groups = (n_frames + 31) / 32;
     const dim3 grid((K + 127) / 128, groups);
-    unpack_bits_kernel<<<grid, 128, 0, s>>>(words, scr, out, stride, K, n_frames);
+    unpack_bits_kernel<<<grid, 128, 0, s>>>(words, scr, out, stride, K, n_frames); count_launch();
     return cudaGetLastError();
 }
 
@@ -1427,7 +1438,7 @@ launch_unpack_bytes(const uint32_t* words, const uint8_t* scr, uint8_t* out, int
     if (K % 8) return cudaErrorInvalidValue;
     const int groups = (n_frames + 31) / 32;
     const dim3 grid((K / 8 + 127) / 128, groups);
-    unpack_bytes_kernel<<<grid, 128, 0, s>>>(words, scr, out, stride, K / 8, n_frames);
+    unpack_bytes_kernel<<<grid, 128, 0, s>>>(words, scr, out, stride, K / 8, n_frames); count_launch();
     return cudaGetLastError();
 }
 
@@ -1436,7 +1447,7 @@ launch_pack_bits(const int32_t* in, uint32_t* words, int stride, int N, int n_fr
 {
     const int groups = (n_frames + 31) / 32;
     const dim3 grid((N + 31) / 32, groups), block(32, 8);
-    pack_bits_kernel<<<grid, block, 0, s>>>(in, words, stride, N, n_frames);
+    pack_bits_kernel<<<grid, block, 0, s>>>(in, words, stride, N, n_frames); count_launch();
     return cudaGetLastError();
 }
 } // namespace dvbs2

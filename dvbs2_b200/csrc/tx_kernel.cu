@@ -208,17 +208,17 @@ __global__ void __launch_bounds__(128) monitor_kernel(const uint32_t* __restrict
 cudaError_t
 launch_tx_random_payload(uint32_t* src, int K, int n_groups, uint64_t seed, cudaStream_t s)
 {
-    tx_random_payload_kernel<<<148 * 8, 256, 0, s>>>(src, K, n_groups, seed);
+    tx_random_payload_kernel<<<148 * 8, 256, 0, s>>>(src, K, n_groups, seed); count_launch();
     return cudaGetLastError();
 }
 
 cudaError_t
 launch_tx_encode(const TxLaunch& a, cudaStream_t s)
 {
-    tx_bch_encode_kernel<<<(a.n_groups + 3) / 4, 128, 0, s>>>(a.src, a.cw, a.scr, a.gmask, a.K_bch, a.N_bch, a.n_groups);
+    tx_bch_encode_kernel<<<(a.n_groups + 3) / 4, 128, 0, s>>>(a.src, a.cw, a.scr, a.gmask, a.K_bch, a.N_bch, a.n_groups); count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    tx_ldpc_encode_kernel<<<a.n_groups, 256, 0, s>>>(a.cw, a.idx, a.N_bch, N_LDPC - a.N_bch, a.d_info, a.d_pad);
+    tx_ldpc_encode_kernel<<<a.n_groups, 256, 0, s>>>(a.cw, a.idx, a.N_bch, N_LDPC - a.N_bch, a.d_info, a.d_pad); count_launch();
     return cudaGetLastError();
 }
 
@@ -227,14 +227,14 @@ launch_tx_modulate_awgn(const TxLaunch& a, const float* cstl, float* sym, float*
                         int itl_rev, float sigma, uint64_t seed, cudaStream_t s)
 {
     const dim3 grid(a.n_frames, (n_sym + 255) / 256);
-    tx_modulate_awgn_kernel<<<grid, 256, 0, s>>>(a.cw, cstl, sym, cp, bps, n_sym, itl_cols, itl_rev, a.n_frames, sigma, seed);
+    tx_modulate_awgn_kernel<<<grid, 256, 0, s>>>(a.cw, cstl, sym, cp, bps, n_sym, itl_cols, itl_rev, a.n_frames, sigma, seed); count_launch();
     return cudaGetLastError();
 }
 
 cudaError_t
 launch_monitor(const uint32_t* dec, int dec_stride, const TxLaunch& a, unsigned long long* mon, cudaStream_t s)
 {
-    monitor_kernel<<<(a.n_groups + 3) / 4, 128, 0, s>>>(dec, dec_stride, a.src, a.scr, a.K_bch, a.n_frames, a.n_groups, mon);
+    monitor_kernel<<<(a.n_groups + 3) / 4, 128, 0, s>>>(dec, dec_stride, a.src, a.scr, a.K_bch, a.n_frames, a.n_groups, mon); count_launch();
     return cudaGetLastError();
 }
 } // namespace dvbs2

@@ -11,6 +11,8 @@
 #define DVBS2_B200_CUDA_HANDLE_HPP_
 
 #include <atomic>
+#include <cstdlib>
+#include <map>
 #include <sstream>
 #include <string>
 
@@ -38,6 +40,8 @@ class Cuda_handle
     dvbs2_cuda_cfg cfg_;
     dvbs2_cuda_handle* h_;
     dvbs2_cuda_info info_;
+    std::map<const void*, size_t> pinned_; // socket buffers registered by this handle (0 bytes: registration refused, not retried)
+    bool pin_enabled_;
 
     static int next_device()
     {
@@ -51,6 +55,7 @@ class Cuda_handle
     explicit Cuda_handle(const dvbs2_cuda_cfg& cfg)
       : cfg_(cfg)
       , h_(nullptr)
+      , pin_enabled_(std::getenv("DVBS2_CUDA_NO_PIN") == nullptr)
     {
         if (cfg_.device < 0) cfg_.device = next_device();
         const int rc = dvbs2_cuda_create(&cfg_, &h_);
@@ -66,7 +71,41 @@ class Cuda_handle
     }
     Cuda_handle(const Cuda_handle&) = delete;
     Cuda_handle& operator=(const Cuda_handle&) = delete;
-    ~Cuda_handle() { dvbs2_cuda_destroy(h_); }
+    ~Cuda_handle()
+    {
+        unpin_all();
+        dvbs2_cuda_destroy(h_);
+    }
+
+    /*!
+     * Page-locks a socket buffer the first time a codelet sees it (cudaHostRegister through the C ABI), so that the
+     * library's chunked cudaMemcpyAsync calls run at PCIe rate and overlap with the kernels instead of being staged
+     * through the driver's bounce buffer.  Socket buffers are std::vector<uint8_t> owned by the producing task and stay
+     * put after binding (lib/streampu/include/Runtime/Socket/Socket.hxx:1007-1011); set_n_frames() reallocates them, so
+     * the modules call unpin_all() there.  A refused registration (e.g. the neighbouring GPU module already pinned the
+     * shared buffer) is not an error: the copy takes the pageable path.  DVBS2_CUDA_NO_PIN=1 disables pinning.
+     */
+    void pin(const void* ptr, const size_t bytes)
+    {
+        if (!pin_enabled_ || ptr == nullptr || bytes < (size_t)1 << 16) return;
+        auto it = pinned_.find(ptr);
+        if (it != pinned_.end() && (it->second == 0 || it->second >= bytes)) return;
+        if (it != pinned_.end()) dvbs2_cuda_host_unregister(h_, const_cast<void*>(ptr));
+        pinned_[ptr] = dvbs2_cuda_host_register(h_, const_cast<void*>(ptr), bytes) == DVBS2_OK ? bytes : 0;
+    }
+    void unpin_all()
+    {
+        for (auto& kv : pinned_)
+            if (kv.second) dvbs2_cuda_host_unregister(h_, const_cast<void*>(kv.first));
+        pinned_.clear();
+    }
+    size_t n_pinned() const
+    {
+        size_t n = 0;
+        for (auto& kv : pinned_)
+            n += kv.second != 0;
+        return n;
+    }
 
     dvbs2_cuda_handle* get() const { return h_; }
     const dvbs2_cuda_cfg& cfg() const { return cfg_; }

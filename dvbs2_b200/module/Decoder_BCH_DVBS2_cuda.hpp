@@ -58,6 +58,7 @@ class Decoder_BCH_DVBS2_cuda : public aff3ct::module::Decoder_HIHO<B>
 
     virtual void set_n_frames(const size_t n_frames)
     {
+        this->handle->unpin_all(); // the sockets are about to be reallocated
         aff3ct::module::Decoder_HIHO<B>::set_n_frames(n_frames);
         if ((int)n_frames > this->handle->info().max_frames)
             this->handle = std::make_shared<Cuda_handle>(this->handle->cfg_for((int)n_frames, this->handle->cfg().device));
@@ -74,6 +75,8 @@ class Decoder_BCH_DVBS2_cuda : public aff3ct::module::Decoder_HIHO<B>
     virtual int _decode_hiho(const B* Y_N, int8_t* CWD, B* V_K, const size_t frame_id)
     {
         const int n = (int)this->get_n_frames_per_wave();
+        this->handle->pin(Y_N, sizeof(B) * (size_t)n * this->N);
+        this->handle->pin(V_K, sizeof(B) * (size_t)n * this->K);
         DVBS2_B200_CHECK(this->handle, dvbs2_cuda_bch_decode_hiho(this->handle->get(), Y_N, CWD, V_K, n));
         int status = 0;
         for (int f = 0; f < n; f++)

@@ -85,6 +85,7 @@ class Decoder_LDPC_DVBS2_cuda : public aff3ct::module::Decoder_SIHO<B, R>
 
     virtual void set_n_frames(const size_t n_frames)
     {
+        this->handle->unpin_all(); // the sockets are about to be reallocated
         aff3ct::module::Decoder_SIHO<B, R>::set_n_frames(n_frames);
         if ((int)n_frames > this->handle->info().max_frames) // (re)allocate device buffers, as DVBS2.cpp:447 expects
             this->handle = std::make_shared<Cuda_handle>(this->handle->cfg_for((int)n_frames, this->handle->cfg().device));
@@ -104,6 +105,8 @@ class Decoder_LDPC_DVBS2_cuda : public aff3ct::module::Decoder_SIHO<B, R>
     virtual int _decode_siho(const R* Y_N, int8_t* CWD, B* V_K, const size_t frame_id)
     {
         const int n = (int)this->get_n_frames_per_wave();
+        this->handle->pin(Y_N, sizeof(R) * (size_t)n * DVBS2_N_LDPC);
+        this->handle->pin(V_K, sizeof(B) * (size_t)n * this->K);
         DVBS2_B200_CHECK(this->handle, dvbs2_cuda_ldpc_decode_siho(this->handle->get(), Y_N, CWD, V_K, nullptr, n));
         int status = 0; // like the SIMD decoders: non-zero when some frame of the wave is not a codeword
         for (int f = 0; f < n; f++)

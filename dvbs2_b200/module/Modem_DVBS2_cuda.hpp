@@ -57,6 +57,7 @@ class Modem_DVBS2_cuda : public aff3ct::module::Modem<B, R, Q>
 
     virtual void set_n_frames(const size_t n_frames)
     {
+        this->handle->unpin_all(); // the sockets are about to be reallocated
         aff3ct::module::Modem<B, R, Q>::set_n_frames(n_frames);
         if ((int)n_frames > this->handle->info().max_frames)
             this->handle = std::make_shared<Cuda_handle>(this->handle->cfg_for((int)n_frames, this->handle->cfg().device));
@@ -73,6 +74,8 @@ class Modem_DVBS2_cuda : public aff3ct::module::Modem<B, R, Q>
     virtual void _demodulate(const float* CP, const Q* Y_N1, Q* Y_N2, const size_t frame_id)
     {
         const int n = (int)this->get_n_frames_per_wave();
+        this->handle->pin(Y_N1, sizeof(Q) * (size_t)n * this->N_fil);
+        this->handle->pin(Y_N2, sizeof(Q) * (size_t)n * this->N);
         DVBS2_B200_CHECK(this->handle, dvbs2_cuda_demodulate(this->handle->get(), CP, Y_N1, Y_N2, n));
         (void)frame_id;
     }

@@ -89,6 +89,8 @@ class Receiver_chain_DVBS2_cuda : public spu::module::Stateful
               auto& c = static_cast<Receiver_chain_DVBS2_cuda&>(m);
               const int n = (int)c.get_n_frames_per_wave();
               int8_t* cwd = static_cast<int8_t*>(t[ps_CWD2].get_dataptr());
+              c.handle->pin(t[ps_Y_N1].get_dataptr(), sizeof(float) * (size_t)n * dvbs2_cuda_pl_frame_size(c.handle->get()));
+              c.handle->pin(t[ps_V_K].get_dataptr(), sizeof(int32_t) * (size_t)n * c.handle->info().K_bch);
               DVBS2_B200_CHECK(c.handle,
                                dvbs2_cuda_rx_chain(c.handle->get(), static_cast<float*>(t[ps_Y_N1].get_dataptr()), nullptr,
                                                    static_cast<float*>(t[ps_SIG].get_dataptr()),
@@ -117,6 +119,7 @@ class Receiver_chain_DVBS2_cuda : public spu::module::Stateful
 
     virtual void set_n_frames(const size_t n_frames)
     {
+        this->handle->unpin_all(); // the sockets are about to be reallocated
         spu::module::Stateful::set_n_frames(n_frames);
         if ((int)n_frames > this->handle->info().max_frames)
             this->handle = std::make_shared<Cuda_handle>(this->handle->cfg_for((int)n_frames, this->handle->cfg().device));

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <memory>
@@ -33,6 +34,7 @@
 
 #include "Decoder_BCH_DVBS2_cuda.hpp"
 #include "Decoder_LDPC_DVBS2_cuda.hpp"
+#include "Adaptor_DVBS2_cuda.hpp"
 #include "Decoder_chain_DVBS2_cuda.hpp"
 #include "Modem_DVBS2_cuda.hpp"
 #include "Receiver_chain_DVBS2_cuda.hpp"
@@ -364,6 +366,65 @@ main(int argc, char** argv)
                "fused GPU module: FE agrees with the all-CPU chain (its own demapper) up to LLR rounding");
         expect(cnt->accepted_wrong.load() == 0 || cpu_fe > 0, "BCH-accepted frames carry the payload");
 
+        // ------------------------------------------------------------------ compact sockets: IQ_packer<sc16> ->
+        //        Decoder_chain_compact_DVBS2_cuda<int16_t> -> Bit_unpacker in a 2-thread Sequence; and, stand-alone, the compact
+        //        stage against the float-socket stage on the same sample values (must be bit-identical)
+        long cq_frames = 0, cq_be = 0, cq_fe = 0;
+        size_t n_pinned = 0;
+        {
+            using namespace dvbs2_b200;
+            const float scale = 1.f / 4096.f;
+            pool->next = 0;
+            auto cnt2 = std::make_shared<Counters>();
+            Pool_source src2(pool);
+            IQ_packer<int16_t> packer(n_sym2, scale, F);
+            Decoder_chain_compact_DVBS2_cuda<int16_t> cchain(modcod, 10, "NMS", 1.f, true, F, -1, scale, true);
+            Bit_unpacker unpacker(mc.K_bch, F);
+            Bit_counter counter2(cnt2, mc.K_bch, F);
+            packer["pack::Y_N1"] = src2["generate::Y_N1"];
+            cchain[chc::sck::demodulate_decode::CP] = src2["generate::CP"];
+            cchain[chc::sck::demodulate_decode::Y_N1] = packer["pack::Y_N2"];
+            unpacker["unpack::X"] = cchain[chc::sck::demodulate_decode::V_K];
+            counter2["check::U"] = src2["generate::U_K"];
+            counter2["check::V"] = unpacker["unpack::Y"];
+            counter2["check::CWD"] = cchain[chc::sck::demodulate_decode::CWD_bch];
+            counter2["check::VALID"] = src2["generate::VALID"];
+            spu::runtime::Sequence seq2(src2("generate"), 2);
+            seq2.exec([&]() { return pool->next.load() >= n_batches + 2; });
+            cq_frames = cnt2->frames.load(), cq_be = cnt2->be.load(), cq_fe = cnt2->fe.load();
+            expect(cq_frames == P, "compact stage in a 2-thread Sequence processed every pool frame exactly once");
+            expect(cq_fe == ref_fe || std::labs(cq_fe - ref_fe) <= 1 + ref_fe / 10,
+                   "compact stage (sc16 symbols, packed payload): FE agrees with the float-socket stage up to the 16-bit samples");
+            // stand-alone, whole pool at once: compact stage == float stage on the very same sample values
+            std::vector<int16_t> q((size_t)P * n_sym2);
+            std::vector<float> deq((size_t)P * n_sym2);
+            for (size_t i = 0; i < q.size(); i++)
+            {
+                q[i] = iq_pack_one<int16_t>(pool->sym[i], 1.f / scale);
+                deq[i] = (float)q[i] * scale;
+            }
+            Decoder_chain_DVBS2_cuda fchain(modcod, 10, "NMS", 1.f, true, P);
+            Decoder_chain_compact_DVBS2_cuda<int16_t> c2(modcod, 10, "NMS", 1.f, true, P, -1, scale, false);
+            fchain[chn::sck::demodulate_decode::CP].bind(pool->sigma);
+            fchain[chn::sck::demodulate_decode::Y_N1].bind(deq);
+            fchain[chn::tsk::demodulate_decode].exec();
+            c2[chc::sck::demodulate_decode::CP].bind(pool->sigma);
+            c2[chc::sck::demodulate_decode::Y_N1].bind(q);
+            c2[chc::tsk::demodulate_decode].exec();
+            const int32_t* vf = static_cast<int32_t*>(fchain[chn::sck::demodulate_decode::V_K].get_dataptr());
+            const uint8_t* vc = static_cast<uint8_t*>(c2[chc::sck::demodulate_decode::V_K].get_dataptr());
+            bool same = true;
+            for (size_t f = 0; f < (size_t)P && same; f++)
+                for (int i = 0; i < mc.K_bch && same; i++)
+                    same = vf[f * mc.K_bch + i] == ((vc[f * (mc.K_bch / 8) + (i >> 3)] >> (i & 7)) & 1);
+            expect(same, "compact stage == float-socket stage bit for bit on the same sample values");
+            expect(std::memcmp(fchain[chn::sck::demodulate_decode::CWD_bch].get_dataptr(),
+                               c2[chc::sck::demodulate_decode::CWD_bch].get_dataptr(), P) == 0,
+                   "compact stage: same CWD as the float-socket stage");
+            n_pinned = fchain.get_handle().n_pinned() + c2.get_handle().n_pinned();
+            expect(n_pinned >= 2, "the modules page-locked their socket buffers on first use (cudaHostRegister)");
+        }
+
         // ------------------------------------------------------------------ receiver stage from PL frames (main.cpp:86-92)
         long rx_be = 0, rx_fe = 0, rxc_be = 0, rxc_fe = 0;
         double sig_rel = 0;
@@ -414,9 +475,11 @@ main(int argc, char** argv)
 
         printf("{\"modcod\": \"%s\", \"frames\": %d, \"demod_max_rel_err\": %.3g, \"ldpc_fe_cpu\": %d, \"bch_fe_cpu\": %ld, "
                "\"seq_frames\": %ld, \"seq_be\": %ld, \"seq_fe\": %ld, \"ref_be\": %ld, \"ref_fe\": %ld, \"cpu_be\": %ld, \"cpu_fe\": %ld, "
-               "\"rx_stage_sigma_rel\": %.3g, \"rx_stage_fe\": %ld, \"rx_stage_fe_cpu\": %ld, \"failures\": %d}\n",
+               "\"rx_stage_sigma_rel\": %.3g, \"rx_stage_fe\": %ld, \"rx_stage_fe_cpu\": %ld, \"compact_frames\": %ld, \"compact_fe\": %ld, "
+               "\"pinned_sockets\": %zu, \"failures\": %d}\n",
                modcod.c_str(), P, max_rel, (int)std::count(c_seq.begin(), c_seq.end(), 0), cpu_fe, cnt->frames.load(),
-               cnt->be.load(), cnt->fe.load(), ref_be, ref_fe, cpu_be, cpu_fe, sig_rel, rx_fe, rxc_fe, failures);
+               cnt->be.load(), cnt->fe.load(), ref_be, ref_fe, cpu_be, cpu_fe, sig_rel, rx_fe, rxc_fe, cq_frames, cq_fe, n_pinned,
+               failures);
     }
     catch (const std::exception& e)
     {

@@ -13,6 +13,10 @@ spu::tools::length_error), a CUDA failure raises capi.Dvbs2CudaError (the refere
 The C++ twins that really derive from aff3ct::module::* live in module/ (see INTEGRATION.md).
 
 Host buffers are numpy arrays; the *_dev methods take torch CUDA tensors and run asynchronously on the handle's stream.
+Stream-ordering contract of the *_dev methods: the handle launches on its OWN non-blocking stream (Handle.stream()), which
+does not synchronise with torch's current stream.  Whatever produced the input tensors (and zero-filled the outputs) on
+torch's stream must have finished first — call torch.cuda.synchronize(), or do the torch work under
+torch.cuda.ExternalStream(h.stream()) — and results are valid after Handle.sync().
 """
 import ctypes as C
 
@@ -34,8 +38,8 @@ def _np_ptr(a, dtype, n_elem, name):
 def _dev_ptr(t, dtype_name, n_elem, name):
     import torch
 
-    want = {"float32": torch.float32, "int32": torch.int32, "int16": torch.int16, "int8": torch.int8,
-            "uint8": torch.uint8}[dtype_name]
+    want = {"float32": torch.float32, "float16": torch.float16, "int32": torch.int32, "int16": torch.int16,
+            "int8": torch.int8, "uint8": torch.uint8}[dtype_name]
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == want and t.is_contiguous()):
         raise ValueError("'%s' must be a contiguous CUDA tensor of %s" % (name, dtype_name))
     if t.numel() != n_elem:
@@ -97,7 +101,9 @@ class Handle:
     def stats(self):
         st = capi.Stats()
         self.check(self.lib.dvbs2_cuda_get_stats(self._h, C.byref(st)))
-        return {n: int(getattr(st, n)) for n, _ in capi.Stats._fields_}
+        out = {n: int(getattr(st, n)) for n, _ in capi.Stats._fields_ if n != "iter_hist"}
+        out["iter_hist"] = [int(x) for x in st.iter_hist]  # frames that left the LDPC decoder after i iterations
+        return out
 
     def reset_stats(self):
         self.check(self.lib.dvbs2_cuda_reset_stats(self._h))
@@ -257,6 +263,95 @@ class Decoder_chain_DVBS2_cuda(_Module):
             None if CWD_bch is None else _dev_ptr(CWD_bch, "int8", F, "CWD_bch"),
             _dev_ptr(V_K_packed, "uint8", F * (self.K // 8), "V_K_packed"),
             None if n_iter is None else _dev_ptr(n_iter, "int32", F, "n_iter"), int(bool(descramble)), F))
+
+
+IQ_DTYPE = {"f32": np.float32, "f16": np.float16, "sc16": np.int16, "sc8": np.int8}
+
+
+def iq_pack(Y_N1, iq_format, iq_scale=1.0):
+    """float I/Q -> wire format, what the upstream adaptor (module/Adaptor_DVBS2_cuda.hpp, task `pack`) does on the host:
+    f16 = IEEE round-to-nearest; sc16 / sc8 = round-half-away(x / scale) saturated to the type (a radio's ADC word)."""
+    Y_N1 = np.asarray(Y_N1, np.float32)
+    if iq_format == "f32":
+        return Y_N1
+    if iq_format == "f16":
+        return Y_N1.astype(np.float16)
+    lim = 32767 if iq_format == "sc16" else 127
+    q = Y_N1 * (np.float32(1.0) / np.float32(iq_scale))  # same two float operations as IQ_packer<Q> (Adaptor_DVBS2_cuda.hpp)
+    q = np.sign(q) * np.floor(np.abs(q) + np.float32(0.5))
+    return np.clip(q, -lim, lim).astype(IQ_DTYPE[iq_format])
+
+
+def iq_unpack(Y, iq_format, iq_scale=1.0):
+    """wire format -> the float samples the device computes with ((float)x * scale, one rounded multiply)"""
+    if iq_format in ("f32", "f16"):
+        return np.asarray(Y).astype(np.float32)
+    return np.asarray(Y).astype(np.float32) * np.float32(iq_scale)
+
+
+class Decoder_chain_compact_DVBS2_cuda(_Module):
+    """The fused stage behind compact sockets: symbols as f16 / sc16 / sc8 instead of float (XFEC frames, or
+    whole PL frames with pl_frames=True), payload as packed bytes instead of int32 per bit."""
+
+    def __init__(self, handle, n_frames=1, iq_format="sc16", iq_scale=1.0 / 8192, pl_frames=False):
+        super().__init__(handle, n_frames)
+        if iq_format not in capi.IQ_FORMAT:
+            raise ValueError("'iq_format' has to be one of %s" % sorted(capi.IQ_FORMAT))
+        self.K = handle.info["K_bch"]
+        self.iq_format, self.iq_scale, self.pl_frames = iq_format, float(iq_scale), bool(pl_frames)
+        self.N_fil = (handle.lib.dvbs2_cuda_pl_frame_size(handle._h) if pl_frames else 2 * handle.info["n_sym"])
+        assert handle.lib.dvbs2_cuda_iq_frame_bytes(handle._h, capi.IQ_FORMAT[iq_format], int(pl_frames)) == \
+            self.N_fil * np.dtype(IQ_DTYPE[iq_format]).itemsize
+
+    def demodulate_decode(self, CP, Y_N1, CWD_ldpc=None, CWD_bch=None, V_K=None, V_K_packed=None, n_iter=None, descramble=False,
+                          SIG=None):
+        F, h = self.n_frames, self.h
+        opt = lambda a, dt, n, name: None if a is None else _np_ptr(a, dt, n, name)  # noqa: E731
+        h.check(h.lib.dvbs2_cuda_chain_compact(
+            h._h, capi.IQ_FORMAT[self.iq_format], self.iq_scale, opt(CP, np.float32, F, "CP"),
+            _np_ptr(Y_N1, IQ_DTYPE[self.iq_format], F * self.N_fil, "Y_N1"), opt(SIG, np.float32, F, "SIG"),
+            opt(CWD_ldpc, np.int8, F, "CWD_ldpc"), opt(CWD_bch, np.int8, F, "CWD_bch"), opt(V_K, np.int32, F * self.K, "V_K"),
+            opt(V_K_packed, np.uint8, F * (self.K // 8), "V_K_packed"), int(bool(descramble)),
+            opt(n_iter, np.int32, F, "n_iter"), int(self.pl_frames), F))
+
+    def demodulate_decode_dev(self, CP, Y_N1, CWD_ldpc=None, CWD_bch=None, V_K=None, V_K_packed=None, n_iter=None,
+                              descramble=False, SIG=None):
+        F, h = self.n_frames, self.h
+        name = {"f32": "float32", "f16": "float16", "sc16": "int16", "sc8": "int8"}[self.iq_format]
+        opt = lambda a, dt, n, nm: None if a is None else _dev_ptr(a, dt, n, nm)  # noqa: E731
+        h.check(h.lib.dvbs2_cuda_chain_compact_dev(
+            h._h, capi.IQ_FORMAT[self.iq_format], self.iq_scale, opt(CP, "float32", F, "CP"),
+            _dev_ptr(Y_N1, name, F * self.N_fil, "Y_N1"), opt(SIG, "float32", F, "SIG"), opt(CWD_ldpc, "int8", F, "CWD_ldpc"),
+            opt(CWD_bch, "int8", F, "CWD_bch"), opt(V_K, "int32", F * self.K, "V_K"),
+            opt(V_K_packed, "uint8", F * (self.K // 8), "V_K_packed"), int(bool(descramble)),
+            opt(n_iter, "int32", F, "n_iter"), int(self.pl_frames), F))
+
+
+class Decoder_llr8_DVBS2_cuda(_Module):
+    """Fixed-point decode stage from int8 LLRs (Quantizer_pow2 outputs): int16 LDPC decode_siho -> BCH decode_hiho
+    (-> BB descramble), int32 bits or packed bytes out.  The handle must use precision "i16"."""
+
+    def __init__(self, handle, n_frames=1):
+        super().__init__(handle, n_frames)
+        self.K, self.N = handle.info["K_bch"], N_LDPC
+
+    def decode(self, Y_N, CWD_ldpc=None, CWD_bch=None, V_K=None, V_K_packed=None, n_iter=None, descramble=False):
+        F, h = self.n_frames, self.h
+        opt = lambda a, dt, n, name: None if a is None else _np_ptr(a, dt, n, name)  # noqa: E731
+        h.check(h.lib.dvbs2_cuda_decode_llr8(
+            h._h, _np_ptr(Y_N, np.int8, F * self.N, "Y_N"), opt(CWD_ldpc, np.int8, F, "CWD_ldpc"),
+            opt(CWD_bch, np.int8, F, "CWD_bch"), opt(V_K, np.int32, F * self.K, "V_K"),
+            opt(V_K_packed, np.uint8, F * (self.K // 8), "V_K_packed"), int(bool(descramble)),
+            opt(n_iter, np.int32, F, "n_iter"), F))
+
+    def decode_dev(self, Y_N, CWD_ldpc=None, CWD_bch=None, V_K=None, V_K_packed=None, n_iter=None, descramble=False):
+        F, h = self.n_frames, self.h
+        opt = lambda a, dt, n, nm: None if a is None else _dev_ptr(a, dt, n, nm)  # noqa: E731
+        h.check(h.lib.dvbs2_cuda_decode_llr8_dev(
+            h._h, _dev_ptr(Y_N, "int8", F * self.N, "Y_N"), opt(CWD_ldpc, "int8", F, "CWD_ldpc"),
+            opt(CWD_bch, "int8", F, "CWD_bch"), opt(V_K, "int32", F * self.K, "V_K"),
+            opt(V_K_packed, "uint8", F * (self.K // 8), "V_K_packed"), int(bool(descramble)),
+            opt(n_iter, "int32", F, "n_iter"), F))
 
 
 class Framer_DVBS2_cuda(_Module):

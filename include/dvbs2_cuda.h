@@ -113,7 +113,9 @@ extern "C"
         uint64_t ldpc_failures;   /* frames whose syndrome was non-zero after the last iteration            */
         uint64_t bch_nonzero;     /* frames entering Berlekamp (non-zero BCH syndrome)                      */
         uint64_t bch_failures;    /* frames BCH could not correct                                           */
-        uint64_t kernel_launches; /* kernels launched by this handle                                        */
+        uint64_t kernel_launches; /* kernels launched by this handle (counted at every launch site)         */
+        uint64_t iter_hist[33];   /* early-stop histogram: frames that left the LDPC decoder after i iterations
+                                   * (i = 1 .. 31; bin 32 collects >= 32; bin 0 stays 0)                    */
     } dvbs2_cuda_stats;
 
     /* device time per stage, measured with CUDA events recorded on the launching stream around each kernel of the
@@ -159,6 +161,45 @@ extern "C"
      * (dvbs2_cuda_host_register) for full PCIe rate. */
     int dvbs2_cuda_chain(dvbs2_cuda_handle* h, const float* CP, const float* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
                          int32_t* V_K, int32_t* n_iter, int n_frames);
+
+    /* ---- compact socket formats --------------------------------------------------------------------
+     * AFF3CT's sockets carry float symbols / LLRs and one int32 per bit (A/include/Tools/types.h:11-27; buffers are
+     * std::vector<uint8_t> per socket, S/include/Runtime/Socket/Socket.hxx:1007-1011): 64.8 KB in and 56.9 KB out per
+     * QPSK-S_8/9 frame, which is what bounds the stage once it sits behind PCIe.  The entry points below move the same
+     * information in fewer bytes; dvbs2_b200/module/Adaptor_DVBS2_cuda.hpp holds the StreamPU modules that convert at the
+     * stage's edges (float I/Q -> wire format upstream, packed bytes -> int32 bits downstream). */
+    typedef enum
+    {
+        DVBS2_IQ_F32 = 0,  /* float I, float Q: the reference socket (8 B / symbol)                                    */
+        DVBS2_IQ_F16 = 1,  /* IEEE binary16 I/Q (4 B / symbol); converted exactly to float on the device               */
+        DVBS2_IQ_SC16 = 2, /* int16 I/Q x iq_scale (4 B / symbol), the USRP/UHD "sc16" wire format                      */
+        DVBS2_IQ_SC8 = 3   /* int8 I/Q x iq_scale (2 B / symbol), UHD "sc8"                                             */
+    } dvbs2_iq_format;
+    /* bytes of one frame's symbols in that format (XFEC frame, or PL frame when pl_frames != 0) */
+    size_t dvbs2_cuda_iq_frame_bytes(const dvbs2_cuda_handle* h, int iq_format, int pl_frames);
+
+    /* dvbs2_cuda_chain / dvbs2_cuda_rx_chain with the symbols in a compact wire format.  Y_N1[F][2*n_sym] (or whole PL
+     * frames when pl_frames != 0) holds iq_format elements; integer samples are converted as (float)x * iq_scale — one
+     * rounded multiply, exactly what a host adaptor in front of Modem::demodulate would compute — so for the same sample
+     * values the results are bit-identical to the float entry points.  CP == NULL (PL frames only): sigma from the
+     * on-device Estimator_DVBS2, returned in SIG if given.  Exactly one of V_K (int32 per bit) and V_K_packed
+     * ([F][K_bch/8], Bit_packer layout) must be given. */
+    int dvbs2_cuda_chain_compact(dvbs2_cuda_handle* h, int iq_format, float iq_scale, const float* CP, const void* Y_N1,
+                                 float* SIG, int8_t* CWD_ldpc, int8_t* CWD_bch, int32_t* V_K, uint8_t* V_K_packed,
+                                 int descramble, int32_t* n_iter, int pl_frames, int n_frames);
+    int dvbs2_cuda_chain_compact_dev(dvbs2_cuda_handle* h, int iq_format, float iq_scale, const float* d_CP,
+                                     const void* d_Y_N1, float* d_SIG, int8_t* d_CWD_ldpc, int8_t* d_CWD_bch, int32_t* d_V_K,
+                                     uint8_t* d_V_K_packed, int descramble, int32_t* d_n_iter, int pl_frames, int n_frames);
+
+    /* Fixed-point decode stage from int8 LLRs: Decoder_SIHO::decode_siho (R = int16_t arithmetic) -> Decoder_HIHO::decode_hiho
+     * (-> Scrambler_BB::descramble).  Y_N[F][16200] int8 are Quantizer_pow2 outputs (the AFF3CT default, 6 bits with 2
+     * fractional, fits int8: A/src/Launcher/Code/LDPC/LDPC.cpp:58-62), a quarter of the float LLR bytes; they are widened
+     * to int16 on the device, so the results equal the reference's int16 decoder on the same values bit for bit.  The handle
+     * must have been created with DVBS2_PREC_I16.  Exactly one of V_K and V_K_packed must be given. */
+    int dvbs2_cuda_decode_llr8(dvbs2_cuda_handle* h, const int8_t* Y_N, int8_t* CWD_ldpc, int8_t* CWD_bch, int32_t* V_K,
+                               uint8_t* V_K_packed, int descramble, int32_t* n_iter, int n_frames);
+    int dvbs2_cuda_decode_llr8_dev(dvbs2_cuda_handle* h, const int8_t* d_Y_N, int8_t* d_CWD_ldpc, int8_t* d_CWD_bch,
+                                   int32_t* d_V_K, uint8_t* d_V_K_packed, int descramble, int32_t* d_n_iter, int n_frames);
 
     /* The same stage with the bit-packed output format: V_K_packed[F][K_bch/8] bytes, bit i of a frame at
      * byte i/8, bit i%8 — the layout of spu::tools::Bit_packer::pack(msb_to_lsb = false) that Sink_user_binary writes

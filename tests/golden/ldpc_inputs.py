@@ -108,3 +108,22 @@ def quantize(llr, dec, bits):
 
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def load_fixture(oracle, modcod):
+    """tests/golden/ldpc256_<modcod>.npz (reference outputs, make_golden_ldpc.py) next to its regenerated inputs:
+    -> (npz, inputs dict, q16, q8, dict of expected bit arrays per decoder key)"""
+    import os
+
+    from oracle.oracle import MODCODS
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ldpc256_%s.npz" % modcod.replace("/", "_")))
+    d = make(oracle, modcod, seed=int(g["seed"]))
+    q16, q8 = quantize(d["llr"], 2, 6), quantize(d["llr"], 1, 6).astype(np.int8)
+    # the inputs are rebuilt from integer hashing + IEEE float32 add/mul/min: a mismatch means numpy changed, not the decoder
+    assert sha(d["llr"]) == str(g["llr_sha"]) and sha(q16) == str(g["q16_sha"]) and sha(q8) == str(g["q8_sha"])
+    N, K = MODCODS[modcod]["N_bch"], MODCODS[modcod]["K_bch"]
+    ub = lambda a, n: np.unpackbits(a, axis=-1)[..., :n].astype(np.int32)  # noqa: E731
+    want = {k[:-2]: ub(g[k], N) ^ d["ldpc"][:, :N] for k in g.files if k.endswith("_x") and k != "bch_x"}
+    want["bch"] = ub(g["bch_x"], K) ^ d["bch"][:, :K]
+    return g, d, q16, q8, want

@@ -21,3 +21,4 @@ def test_cpp_modules_drop_in(modcod, ebn0):
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["failures"] == 0 and d["frames"] == 192 and d["seq_frames"] == 192
     assert d["seq_be"] == d["ref_be"] and d["seq_fe"] == d["ref_fe"] and d["demod_max_rel_err"] <= 1e-4
+    assert d["compact_frames"] == 192 and d["pinned_sockets"] >= 2  # compact-socket stage + page-locked socket buffers

@@ -124,3 +124,46 @@ def test_framer_and_estimator_vs_reference_outputs(modcod):
     assert np.max(np.abs(sig - ref[0]) / ref[0]) < 5e-6
     assert np.allclose(eb, ref[1], rtol=0, atol=2e-4) and np.allclose(es, ref[2], rtol=0, atol=2e-4)
     h.close()
+
+
+@pytest.mark.parametrize("modcod", ALL)
+def test_ldpc_256_frames_per_modcod_vs_reference_outputs(oracle, modcod):
+    """tests/golden/ldpc256_*.npz: 256 frames per MODCOD across the waterfall (FER ~1 -> 0), outputs of the compiled reference
+    classes.  The CUDA path must give the sequential decoders' bits and CWD on every frame (float through all three kernel
+    shapes, int16, int8), the oracle-pinned iteration counts, the bits of both inter-frame SIMD decoders (ONMS_inter a8, the
+    templated ..._inter a9) wherever those converge, and the BCH stage's verdicts behind it."""
+    import sys
+
+    sys.path.insert(0, GOLD)
+    import ldpc_inputs as gi
+    from dvbs2_b200 import Decoder_BCH_DVBS2_cuda, Decoder_LDPC_DVBS2_cuda, Handle
+
+    g, d, q16, q8, want = gi.load_fixture(oracle, modcod)
+    mc = MODCODS[modcod]
+    F, N, K = 256, mc["N_bch"], mc["K_bch"]
+
+    def run(Y, prec, **kw):
+        h = Handle(modcod=modcod, precision=prec, n_frames=F, **kw)
+        V, cwd, nit = np.zeros((F, N), np.int32), np.zeros(F, np.int8), np.zeros(F, np.int32)
+        Decoder_LDPC_DVBS2_cuda(h, F).decode_siho(np.ascontiguousarray(Y), cwd, V, nit)
+        h.close()
+        return V, cwd, nit
+
+    for nf, coop in ((1, 0), (1, -1), (2, -1)):
+        V, cwd, nit = run(d["llr"], "f32", ldpc_frames_per_lane=nf, ldpc_coop_max_frames=coop)
+        assert np.array_equal(cwd, g["seq_f32_cwd"]) and np.array_equal(V, want["seq_f32"]) and np.array_equal(nit, g["seq_f32_nit"])
+        for key in ("onms_f32", "tint_f32"):
+            ok = g[key + "_cwd"] == 1
+            assert np.array_equal(V[ok], want[key][ok])
+    V16, c16, _ = run(q16, "i16")
+    assert np.array_equal(c16, g["seq_i16_cwd"]) and np.array_equal(V16, want["seq_i16"])
+    for key in ("onms_i16", "tint_i16"):
+        ok = g[key + "_cwd"] == 1
+        assert np.array_equal(V16[ok], want[key][ok])
+    V8, c8, _ = run(q8, "i8", quant_dec=1)
+    assert np.array_equal(c8, g["seq_i8_cwd"]) and np.array_equal(V8, want["seq_i8"])
+    h = Handle(modcod=modcod, n_frames=F)
+    Vb, cb = np.zeros((F, K), np.int32), np.zeros(F, np.int8)
+    Decoder_BCH_DVBS2_cuda(h, F).decode_hiho(np.ascontiguousarray(want["seq_f32"]), cb, Vb)
+    h.close()
+    assert np.array_equal(cb, g["bch_cwd"]) and np.array_equal(Vb, want["bch"])

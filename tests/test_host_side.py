@@ -37,7 +37,7 @@ def test_structs_match_header_layout():
     from dvbs2_b200 import capi
 
     lib = _lib()
-    assert C.sizeof(capi.Cfg) == 16 * 4 and C.sizeof(capi.Info) == 9 * 4 and C.sizeof(capi.Stats) == 6 * 8
+    assert C.sizeof(capi.Cfg) == 16 * 4 and C.sizeof(capi.Info) == 9 * 4 and C.sizeof(capi.Stats) == (6 + 33) * 8
     assert C.sizeof(capi.Timers) == 10 * 8 and C.sizeof(capi.Monitor) == 3 * 8
     cfg = capi.Cfg()
     lib.dvbs2_cuda_default_cfg(C.byref(cfg))

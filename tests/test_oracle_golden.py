@@ -161,21 +161,12 @@ def test_framer_and_estimator_match_reference(oracle, modcod):
 
 # ------------------------------------------------------------------------------------------------ 256 frames per MODCOD
 def load256(oracle, modcod):
-    """tests/golden/ldpc256_<modcod>.npz (reference outputs, make_golden_ldpc.py) + its regenerated inputs."""
     import sys
 
     sys.path.insert(0, GOLD)
     import ldpc_inputs as gi
 
-    g = np.load(os.path.join(GOLD, "ldpc256_%s.npz" % modcod.replace("/", "_")))
-    d = gi.make(oracle, modcod, seed=int(g["seed"]))
-    q16, q8 = gi.quantize(d["llr"], 2, 6), gi.quantize(d["llr"], 1, 6).astype(np.int8)
-    # the inputs are rebuilt from integer hashing + IEEE float32 add/mul/min: a mismatch means numpy changed, not the decoder
-    assert gi.sha(d["llr"]) == str(g["llr_sha"]) and gi.sha(q16) == str(g["q16_sha"]) and gi.sha(q8) == str(g["q8_sha"])
-    N, K = MODCODS[modcod]["N_bch"], MODCODS[modcod]["K_bch"]
-    want = {k[:-2]: ub(g[k], N) ^ d["ldpc"][:, :N] for k in g.files if k.endswith("_x") and k != "bch_x"}
-    want["bch"] = ub(g["bch_x"], K) ^ d["bch"][:, :K]
-    return g, d, q16, q8, want
+    return gi.load_fixture(oracle, modcod)
 
 
 @pytest.mark.parametrize("modcod", ALL)
