@@ -52,8 +52,9 @@ def parse():
     p.add_argument("--prec", default="f32", choices=["f32", "i16", "i8"])
     p.add_argument("--ite", type=int, default=10)
     p.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the largest of 3, 2, 1 waves of the LDPC kernel = SMs x 12 warps x 64 frames each that fits in 80 %% of the free HBM)")
-    p.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e step per GPU over all clones (default: two waves; one for the float/int32 sockets)")
-    p.add_argument("--e2e-clones", type=int, default=4)
+    p.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e call of one module clone (default: one wave of the LDPC kernel)")
+    p.add_argument("--e2e-clones", type=int, default=3)
+    p.add_argument("--e2e-chunks", type=int, default=-1, help="host_pipeline_chunks of the e2e clones (-1: 1 when there are several clones, else automatic)")
     p.add_argument("--e2e-sockets", default="", help="comma list of socket formats to time (default: f32_int32,f32_packed,sc16_packed,sc8_packed; llr8_packed with --prec i16)")
     p.add_argument("--no-configs", action="store_true", help="skip the extra lines for BASELINE configs 2-4")
     p.add_argument("--no-numa", action="store_true", help="do not bind this rank to the CPU cores next to its GPU")
@@ -386,6 +387,16 @@ def main():
     e2e = None
     if not args.no_e2e:
         NC = max(1, args.e2e_clones)
+        # device-resident result of the first frames of batch 0 (what clone 0 decodes), then the big decoder state goes: the e2e
+        # clones bring their own handles
+        step(0)
+        h.sync()
+        V_head = V[:min(F, wave)].cpu().numpy()
+        h.close()
+        h = None
+        del V, chain, tx
+        batches = batches[:1]
+        torch.cuda.empty_cache()
         default_fmts = "llr8_packed" if args.prec == "i16" else "f32_int32,f32_packed,sc16_packed,sc8_packed"
         fmts = [f for f in (args.e2e_sockets or default_fmts).split(",") if f]
         SC16, SC8 = 1.0 / 8192, 1.0 / 32  # LSB of the integer I/Q formats: +-4.0 full scale (unit-energy constellations)
@@ -393,14 +404,17 @@ def main():
 
         def e2e_run(fmt):
             in_kind, out_kind = fmt.split("_")
-            # frames per step over all clones: two waves for the compact formats, one for the float / int32 sockets (19 GB of
-            # pinned memory per wave there)
-            waves = 1 if fmt == "f32_int32" else 2
-            Fe = max(256, min(F, args.e2e_frames if args.e2e_frames > 0 else waves * wave) // NC // 256 * 256)
+            # one call of a clone = one wave of the LDPC kernel (every launch fills the machine; the copies of one clone overlap
+            # the kernels of the others, so calls are not chunked).  The reference's int32-per-bit sockets need 14 GB of pinned
+            # memory per wave and clone: half a wave there when eight ranks share one host.
+            Fe = args.e2e_frames if args.e2e_frames > 0 else (wave // 2 if (fmt == "f32_int32" and world > 1) else wave)
+            Fe = max(256, min(F // NC, Fe) // 256 * 256)
             prec = "i16" if in_kind == "llr8" else args.prec
+            chunks = args.e2e_chunks if args.e2e_chunks >= 0 else (1 if NC > 1 else 0)
             clones, same = [], None
             for c in range(NC):
-                hc = Handle(modcod=modcod, n_ite=args.ite, norm=1.0, precision=prec, early_stop=True, n_frames=Fe, device=local, **tune)
+                hc = Handle(modcod=modcod, n_ite=args.ite, norm=1.0, precision=prec, early_stop=True, n_frames=Fe, device=local,
+                            host_pipeline_chunks=chunks, **tune)
                 src_sig, src_rx = batches[0][0][c * Fe:(c + 1) * Fe], batches[0][1][c * Fe:(c + 1) * Fe]
                 hs = pin(Fe, dtype=torch.float32)
                 hs.copy_(src_sig)
@@ -464,9 +478,7 @@ def main():
             n_launch = sum(hc.stats()["kernel_launches"] for hc, _, _, _ in clones)
             fails = sum(int((a["c2"] == 0).sum()) for _, _, a, _ in clones)
             if fmt == "f32_int32":  # the host result of clone 0 equals the device-resident result of the same frames
-                step(0)
-                h.sync()
-                same = bool(np.array_equal(clones[0][2]["V"], V[:Fe].cpu().numpy()))
+                same = bool(np.array_equal(clones[0][2]["V"], V_head[:Fe]))
             in_b = clones[0][2]["x"].nbytes + clones[0][2]["sig"].nbytes
             out_b = clones[0][2]["V"].nbytes + 2 * Fe + 4 * Fe
             for hc, _, _, _ in clones:
@@ -500,7 +512,7 @@ def main():
         if head:
             e2e = dict(socks[head])
             e2e["headline_sockets"] = head
-            e2e["api"] = API.get(head, head) + "; %d concurrent module clones (host threads) x %d frames per call" % (
+            e2e["api"] = API.get(head, head) + "; %d concurrent module clones (host threads) x %d frames per call, one chunk per call" % (
                 NC, e2e["frames_per_step_per_gpu"] // NC)
             e2e["vs_device_resident"] = round(e2e["value"] / value, 4)
             e2e["host_numa"] = numa
@@ -527,9 +539,11 @@ def main():
     # binaries run)
     int16, configs = None, None
     if rank == 0 and world == 1 and args.prec == "f32" and (not args.no_int16 or not args.no_configs):
-        h.close()
-        h = None
-        del batches, V, chain, tx, sig, rx  # sig / rx: the loop variables still hold the last input batch
+        if h is not None:
+            h.close()
+            h = None
+            del V, chain, tx
+        del batches, sig, rx  # sig / rx: the loop variables still hold the last input batch
         torch.cuda.empty_cache()
 
         def sub(workload, prec, extra):

@@ -558,8 +558,9 @@ chunk_frames(const dvbs2_cuda_handle* h, int n_frames)
     // ... but not below four groups per SM: a launch with fewer groups runs one or two warps per SM at the latency of a
     // full one (measured: 12 chunks of 148 groups each took as long as the PCIe traffic they were meant to hide), so calls
     // of up to n_sms * 4 groups are not split at all and rely on the other module clones for overlap
-    int per = (n_frames + N_PIPE - 1) / N_PIPE;
-    per = std::max(per, h->n_sms * 4 * 32 * h->nf);
+    const int want = h->cfg.host_pipeline_chunks > 0 ? std::min(h->cfg.host_pipeline_chunks, N_PIPE) : N_PIPE;
+    int per = (n_frames + want - 1) / want;
+    if (h->cfg.host_pipeline_chunks <= 0) per = std::max(per, h->n_sms * 4 * 32 * h->nf);
     per = (per + 255) / 256 * 256; // whole decoder groups for every precision
     return per;
 }
@@ -651,6 +652,7 @@ extern "C"
             if (cfg->quant_dec <= 0 || cfg->quant_bits < 2 || cfg->quant_dec > cfg->quant_bits || cfg->quant_bits > type_bits)
                 return DVBS2_ERR_INVALID; // Quantizer_pow2.cpp:81-122
         }
+        if (cfg->host_pipeline_chunks < 0 || cfg->host_pipeline_chunks > N_PIPE) return DVBS2_ERR_INVALID;
         if (cfg->ldpc_frames_per_lane != 0 &&
             (cfg->precision != DVBS2_PREC_F32 || (cfg->ldpc_frames_per_lane != 1 && cfg->ldpc_frames_per_lane != 2)))
             return DVBS2_ERR_INVALID;
