@@ -36,7 +36,8 @@ class Cfg(C.Structure):
                 ("early_stop", C.c_int), ("max_frames", C.c_int), ("device", C.c_int), ("quant_bits", C.c_int),
                 ("quant_dec", C.c_int), ("no_compaction", C.c_int), ("compaction_rounds", C.c_int),
                 ("compaction_exit_eighths", C.c_int), ("compaction_nf_later", C.c_int), ("ldpc_frames_per_lane", C.c_int),
-                ("ldpc_coop_max_frames", C.c_int), ("host_pipeline_chunks", C.c_int)]
+                ("ldpc_coop_max_frames", C.c_int), ("ldpc_onchip", C.c_int), ("host_pipeline_chunks", C.c_int),
+                ("reserved", C.c_int * 2)]
 
 
 class Info(C.Structure):

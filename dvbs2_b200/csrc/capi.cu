@@ -96,6 +96,11 @@ struct dvbs2_cuda_handle
     DevBuf in_a, out_a, sigma;
     // transmitter / monitor (allocated on first use)
     DevBuf tx_src, tx_cw, tx_scr, tx_gmask, mon;
+    // on-chip LDPC kernel ("design B"): transposed index table, state of the frames in flight (one region per stream), packed bits
+    uint32_t* d_idxT = nullptr;
+    DevBuf oc_cn, oc_pv, oc_bits;
+    int oc_F = 0;      // frames per CTA
+    int onchip = 0;    // cfg.ldpc_onchip
     int tx_encoded_groups = 0; // 32-frame groups of the current payload that launch_tx_encode has encoded
     uint64_t launches = 0;
     std::string last_error;
@@ -313,6 +318,42 @@ ext_slot_offset(const dvbs2_cuda_handle* h, int f0)
     return ((size_t)std::ceil((double)f0 * sum) + 255) / 256 * 256 + (size_t)256 * (MAX_ROUNDS - 1) * (f0 / 2048);
 }
 
+// Which float calls go to the on-chip kernel when the configuration leaves it open (cfg.ldpc_onchip == 0): see DESIGN.md §4
+// for the measurements behind the rule.
+bool
+call_onchip(const dvbs2_cuda_handle* h, int n_frames)
+{
+    if (h->onchip < 0) return false;
+    if (h->onchip > 0) return true;
+    (void)n_frames;
+    return false; // not the default until it wins on the workload at hand (profiles/README.md)
+}
+
+// on-chip LDPC decode of frame-major LLRs; hard decisions end up in out_hd (bit-sliced), like after run_ldpc_core
+int
+run_ldpc_onchip(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const float* d_llr, int8_t* d_cwd, int32_t* d_nit, int n_frames)
+{
+    int slot = 0;
+    for (int i = 0; i < N_PIPE; i++)
+        if (s == h->pipe[i]) slot = 1 + i;
+    const size_t region = (size_t)h->n_sms * h->oc_F * slot;
+    OnchipLaunch a{};
+    a.llr = d_llr;
+    a.idxT = h->d_idxT;
+    a.cn = (uint4*)h->oc_cn.p + region * h->mc.M;
+    a.pv = (float*)h->oc_pv.p + region * h->mc.M;
+    const int KW = (h->mc.N_bch + 31) / 32;
+    a.out_bits = (uint32_t*)h->oc_bits.p + (size_t)first_frame * KW;
+    a.queue = h->d_queue + 40 + slot;
+    a.cwd = d_cwd, a.n_iter = d_nit, a.stats = (unsigned long long*)h->stats.p;
+    a.n_frames = n_frames, a.K = h->mc.N_bch, a.M = h->mc.M, a.d_info = h->mc.d_info;
+    a.n_ite = h->cfg.n_ite, a.norm = h->cfg.norm, a.early_stop = h->cfg.early_stop, a.n_sms = h->n_sms;
+    CU(h, launch_ldpc_onchip(a, s));
+    CU(h, launch_bits_to_sliced(a.out_bits, (uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC, h->mc.N_bch, N_LDPC,
+                                n_frames, s));
+    return DVBS2_OK;
+}
+
 // LDPC decode of slots [first_frame, first_frame + n_frames): one round, or several rounds with frame compaction in
 // between (at most h->rounds; a round is worth launching only while the previous one had at least two groups)
 int
@@ -410,10 +451,18 @@ run_ldpc(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const void* d_Y,
     if (n_frames == 0) return DVBS2_OK;
     void* var = (char*)h->var.p + (size_t)first_frame * N_LDPC * h->elt;
     const int nf = call_nf(h, n_frames);
-    TRY(prof_mark(h, s, P_PACK));
-    CU(h, launch_pack_llr(d_Y, var, h->cfg.precision, n_frames, nf, s));
-    TRY(prof_mark(h, s, P_LDPC));
-    TRY(run_ldpc_core(h, s, first_frame, n_frames, d_cwd, d_nit, nf));
+    if (call_onchip(h, n_frames))
+    { // the on-chip kernel reads the socket layout directly: no repacking
+        TRY(prof_mark(h, s, P_LDPC));
+        TRY(run_ldpc_onchip(h, s, first_frame, (const float*)d_Y, d_cwd, d_nit, n_frames));
+    }
+    else
+    {
+        TRY(prof_mark(h, s, P_PACK));
+        CU(h, launch_pack_llr(d_Y, var, h->cfg.precision, n_frames, nf, s));
+        TRY(prof_mark(h, s, P_LDPC));
+        TRY(run_ldpc_core(h, s, first_frame, n_frames, d_cwd, d_nit, nf));
+    }
     TRY(prof_mark(h, s, P_UNPACK));
     CU(h, launch_unpack_bits((uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC, d_VK, N_LDPC, h->mc.N_bch, n_frames, s));
     TRY(prof_mark(h, s, P_END));
@@ -452,9 +501,18 @@ run_chain(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const float* d_
         d_sigma = d_sigma_est;
     }
     const int nf = call_nf(h, n_frames);
-    CU(h, launch_demap_to_var(demap_args(h, d_sigma, d_sym, n_frames, pl_frames, iq_fmt, iq_scale), var, h->cfg.precision, nf, s));
-    TRY(prof_mark(h, s, P_LDPC));
-    TRY(run_ldpc_core(h, s, first_frame, n_frames, d_cwd_ldpc, d_nit, nf));
+    if (call_onchip(h, n_frames))
+    { // frame-major LLRs (natural order) into the var buffer, which the on-chip kernel reads as its input
+        CU(h, launch_demap_frames(demap_args(h, d_sigma, d_sym, n_frames, pl_frames, iq_fmt, iq_scale), (float*)var, 1, s));
+        TRY(prof_mark(h, s, P_LDPC));
+        TRY(run_ldpc_onchip(h, s, first_frame, (const float*)var, d_cwd_ldpc, d_nit, n_frames));
+    }
+    else
+    {
+        CU(h, launch_demap_to_var(demap_args(h, d_sigma, d_sym, n_frames, pl_frames, iq_fmt, iq_scale), var, h->cfg.precision, nf, s));
+        TRY(prof_mark(h, s, P_LDPC));
+        TRY(run_ldpc_core(h, s, first_frame, n_frames, d_cwd_ldpc, d_nit, nf));
+    }
     TRY(prof_mark(h, s, P_BCH));
     CU(h, launch_bch_decode(bch_args(h, first_frame, n_frames, d_cwd_bch), h->bch, s));
     TRY(prof_mark(h, s, P_UNPACK));
@@ -616,11 +674,11 @@ extern "C"
         for (DevBuf* b : { &h->var, &h->cn, &h->hd, &h->out_hd, &h->rem, &h->nz, &h->cwd_ldpc, &h->cwd_bch, &h->nit,
                            &h->stats, &h->surv_mask, &h->surv_iters, &h->dst_base, &h->src_of_dst, &h->slot_frame, &h->slot_iters,
                            &h->final_loc, &h->n_surv,
-                           &h->in_a, &h->out_a, &h->sigma, &h->tx_src, &h->tx_cw, &h->tx_scr,
+                           &h->oc_cn, &h->oc_pv, &h->oc_bits, &h->in_a, &h->out_a, &h->sigma, &h->tx_src, &h->tx_cw, &h->tx_scr,
                            &h->tx_gmask, &h->mon })
             if (b->p) cudaFree(b->p);
         for (void* p : { (void*)h->d_idx, (void*)h->d_idx32, (void*)h->d_last, (void*)h->d_queue, (void*)h->d_alpha_to,
-                         (void*)h->d_index_of, (void*)h->d_cstl, (void*)h->d_scr_bytes })
+                         (void*)h->d_index_of, (void*)h->d_cstl, (void*)h->d_scr_bytes, (void*)h->d_idxT })
             if (p) cudaFree(p);
         for (int i = 0; i < N_PIPE; i++)
         {
@@ -653,6 +711,9 @@ extern "C"
                 return DVBS2_ERR_INVALID; // Quantizer_pow2.cpp:81-122
         }
         if (cfg->host_pipeline_chunks < 0 || cfg->host_pipeline_chunks > N_PIPE) return DVBS2_ERR_INVALID;
+        if (cfg->ldpc_onchip < -1 || cfg->ldpc_onchip > 1 || (cfg->ldpc_onchip == 1 && cfg->precision != DVBS2_PREC_F32))
+            return DVBS2_ERR_INVALID;
+        if (cfg->reserved[0] || cfg->reserved[1]) return DVBS2_ERR_INVALID;
         if (cfg->ldpc_frames_per_lane != 0 &&
             (cfg->precision != DVBS2_PREC_F32 || (cfg->ldpc_frames_per_lane != 1 && cfg->ldpc_frames_per_lane != 2)))
             return DVBS2_ERR_INVALID;
@@ -759,6 +820,24 @@ extern "C"
             (rc = ensure(h, h->cwd_ldpc, F)) || (rc = ensure(h, h->cwd_bch, F)) || (rc = ensure(h, h->nit, F * 4)) ||
             (rc = ensure(h, h->stats, STAT_COUNT * sizeof(unsigned long long))))
             return bail(rc);
+        // on-chip LDPC kernel (float): legal while two neighbouring windows of checks share no information variable
+        h->onchip = cfg->precision == DVBS2_PREC_F32 ? cfg->ldpc_onchip : -1;
+        if (h->lt.min_reuse_distance < 2 * ONCHIP_WINDOW)
+        {
+            if (h->onchip == 1) return bail(DVBS2_ERR_INVALID);
+            h->onchip = -1;
+        }
+        if (h->onchip >= 0)
+        {
+            h->oc_F = ldpc_onchip_frames_per_cta(mc.d_info);
+            const std::vector<uint32_t> it = build_onchip_index(h->lt);
+            CUB(cudaMalloc(&h->d_idxT, it.size() * sizeof(uint32_t)));
+            CUB(cudaMemcpy(h->d_idxT, it.data(), it.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            const size_t slots = (size_t)h->n_sms * h->oc_F * (N_PIPE + 1);
+            if ((rc = ensure(h, h->oc_cn, slots * mc.M * sizeof(uint4))) || (rc = ensure(h, h->oc_pv, slots * mc.M * sizeof(float))) ||
+                (rc = ensure(h, h->oc_bits, F * ((mc.N_bch + 31) / 32) * sizeof(uint32_t))))
+                return bail(rc);
+        }
         CUB(cudaMemset(h->stats.p, 0, h->stats.bytes));
         CUB(cudaMemset(h->out_hd.p, 0, h->out_hd.bytes));
         CUB(cudaDeviceSynchronize());

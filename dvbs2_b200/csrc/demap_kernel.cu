@@ -51,19 +51,6 @@ load_sym(const DemapLaunch& a, size_t i)
     else
         return __ldg(a.sym + i);
 }
-// run-time format (the rarely used frame-major demapper and the estimator's staging loop, both warp-uniform)
-__device__ __forceinline__ float
-load_sym_rt(const DemapLaunch& a, size_t i)
-{
-    switch (a.sym_fmt)
-    {
-        case 1: return load_sym<1>(a, i);
-        case 2: return load_sym<2>(a, i);
-        case 3: return load_sym<3>(a, i);
-        default: return load_sym<0>(a, i);
-    }
-}
-
 // LLRs of one received symbol: out[b], b = 0..BPS-1
 template<int BPS>
 __device__ __forceinline__ void
@@ -123,7 +110,7 @@ quantize<float>(float y, float, float)
     return y;
 }
 
-template<int BPS>
+template<int BPS, int FMT>
 __global__ void
 demap_frames_kernel(const DemapLaunch a, float* __restrict__ llr, int deinterleave)
 {
@@ -136,7 +123,7 @@ demap_frames_kernel(const DemapLaunch a, float* __restrict__ llr, int deinterlea
     const float sg = a.sigma[f];
     const float inv = 1.0f / (2 * sg * sg);
     const size_t at = a.pl_sym > 0 ? (size_t)f * 2 * a.pl_sym + 2 * pl_symbol_pos(k, a.n_sym) : (size_t)f * 2 * a.n_sym + 2 * k;
-    const float2 y = make_float2(load_sym_rt(a, at), load_sym_rt(a, at + 1));
+    const float2 y = make_float2(load_sym<FMT>(a, at), load_sym<FMT>(a, at + 1));
     float out[BPS];
     demap_symbol<BPS>(y.x, y.y, inv, cs, out);
     float* o = llr + (size_t)f * N_LDPC;
@@ -345,13 +332,23 @@ cudaError_t
 launch_demap_frames(const DemapLaunch& a, float* llr, int deinterleave, cudaStream_t s)
 {
     const dim3 grid(a.n_frames, (a.n_sym + 255) / 256);
+#define DEMAP_FRAMES(BPS)                                                                                              \
+    switch (a.sym_fmt)                                                                                                 \
+    {                                                                                                                  \
+        case 1: demap_frames_kernel<BPS, 1><<<grid, 256, 0, s>>>(a, llr, deinterleave); break;                         \
+        case 2: demap_frames_kernel<BPS, 2><<<grid, 256, 0, s>>>(a, llr, deinterleave); break;                         \
+        case 3: demap_frames_kernel<BPS, 3><<<grid, 256, 0, s>>>(a, llr, deinterleave); break;                         \
+        default: demap_frames_kernel<BPS, 0><<<grid, 256, 0, s>>>(a, llr, deinterleave); break;                        \
+    }
     switch (a.bps)
     {
-        case 2: demap_frames_kernel<2><<<grid, 256, 0, s>>>(a, llr, deinterleave); count_launch(); break;
-        case 3: demap_frames_kernel<3><<<grid, 256, 0, s>>>(a, llr, deinterleave); count_launch(); break;
-        case 4: demap_frames_kernel<4><<<grid, 256, 0, s>>>(a, llr, deinterleave); count_launch(); break;
+        case 2: DEMAP_FRAMES(2) break;
+        case 3: DEMAP_FRAMES(3) break;
+        case 4: DEMAP_FRAMES(4) break;
         default: return cudaErrorInvalidValue;
     }
+#undef DEMAP_FRAMES
+    count_launch();
     return cudaGetLastError();
 }
 

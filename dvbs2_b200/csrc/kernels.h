@@ -1,6 +1,7 @@
 // Internal launch interfaces between capi.cu and the kernel translation units.
 #pragma once
 #include <cstdint>
+#include <vector>
 #include <cuda_runtime.h>
 
 #include "code_tables.h"
@@ -117,6 +118,32 @@ cudaError_t launch_unpack_bits(const uint32_t* words, int32_t* out, int stride, 
 cudaError_t launch_unpack_bytes(const uint32_t* words, const uint8_t* scr, uint8_t* out, int stride, int K, int n_frames,
                                 cudaStream_t s);
 cudaError_t launch_pack_bits(const int32_t* in, uint32_t* words, int stride, int N, int n_frames, cudaStream_t s);
+
+// ---- "design B": variable nodes on chip (ldpc_onchip_kernel.cu).  Float only; frames come frame-major, bits leave packed
+// per frame and are transposed into the bit-sliced out_hd layout for the BCH stage.
+constexpr int ONCHIP_WINDOW = 26; // checks per window: two neighbouring windows must fit inside min_reuse_distance
+struct OnchipLaunch
+{
+    const float* llr;        // [n_frames][16200] LLRs, natural order
+    const uint32_t* idxT;    // [windows][(d_info+1)/2][32] byte offsets of the information variables, two per word
+    uint4* cn;               // [n_sms * F][M] compressed check state of the frames in flight
+    float* pv;               // [n_sms * F][M] parity variables of the frames in flight
+    uint32_t* out_bits;      // [n_frames][ceil(K/32)] hard decisions, 32 per word
+    int* queue;              // frame queue head (zeroed by the launcher)
+    int8_t* cwd;             // [frames] or null
+    int32_t* n_iter;         // [frames] or null
+    unsigned long long* stats;
+    int n_frames, K, M, d_info;
+    int n_ite;
+    float norm;
+    int early_stop;
+    int n_sms;
+};
+int ldpc_onchip_frames_per_cta(int d_info);
+size_t ldpc_onchip_smem_bytes(int K, int M, int F);
+std::vector<uint32_t> build_onchip_index(const LdpcTables& t);
+cudaError_t launch_ldpc_onchip(const OnchipLaunch& a, cudaStream_t s);
+cudaError_t launch_bits_to_sliced(const uint32_t* bits, uint32_t* out_hd, int K, int stride, int n_frames, cudaStream_t s);
 
 struct DemapLaunch
 {

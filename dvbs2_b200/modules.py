@@ -52,7 +52,7 @@ class Handle:
 
     def __init__(self, modcod="QPSK-S_8/9", n_ite=10, norm=1.0, precision="f32", early_stop=True, n_frames=1024,
                  device=0, quant_bits=6, quant_dec=2, compaction=True, compaction_rounds=0, compaction_exit_eighths=0,
-                 compaction_nf_later=0, ldpc_frames_per_lane=0, ldpc_coop_max_frames=0, host_pipeline_chunks=0):
+                 compaction_nf_later=0, ldpc_frames_per_lane=0, ldpc_coop_max_frames=0, host_pipeline_chunks=0, ldpc_onchip=0):
         self.lib = capi.load()
         if modcod not in capi.MODCOD:
             raise ValueError(str(modcod) + " mod-cod scheme not supported.")  # DVBS2.cpp:319
@@ -68,6 +68,7 @@ class Handle:
         cfg.ldpc_frames_per_lane = int(ldpc_frames_per_lane)
         cfg.ldpc_coop_max_frames = int(ldpc_coop_max_frames)
         cfg.host_pipeline_chunks = int(host_pipeline_chunks)
+        cfg.ldpc_onchip = int(ldpc_onchip)
         self.modcod, self.precision, self.device = modcod, precision, device
         self._h = C.c_void_p()
         rc = self.lib.dvbs2_cuda_create(C.byref(cfg), C.byref(self._h))

@@ -96,11 +96,15 @@ extern "C"
         int ldpc_coop_max_frames;    /* f32 only: calls of up to this many frames (with one frame per lane) use the
                                       * cooperative small-batch LDPC kernel — a CTA per 32-frame group, ~10x shorter calls
                                       * below a few thousand frames, one round, same results; 0 = default 16384, < 0 = never */
+        int ldpc_onchip;             /* f32 only: the on-chip LDPC kernel ("design B", DESIGN.md §4: variable nodes in shared
+                                      * memory, lanes = checks, a chain warp per CTA, no compaction rounds; same results).
+                                      * 0 = automatic (per MODCOD and batch size, from measurements), 1 = always, -1 = never */
         int host_pipeline_chunks;    /* host-buffer entry points: how many chunks a call is split into over the handle's
                                       * pipeline streams (H2D / kernels / D2H of different chunks overlap).  0 = automatic (up
                                       * to 4, never below four decoder groups per SM per chunk); 1 = one chunk per call — the
                                       * right choice when several module clones keep the GPU busy, since the copies of one
                                       * clone then overlap the kernels of the others and every launch fills the machine      */
+        int reserved[2];             /* must be 0 */
     } dvbs2_cuda_cfg;
 
     typedef struct

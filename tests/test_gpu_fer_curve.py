@@ -5,6 +5,7 @@ descrambler, BFER monitor — lands inside the joint binomial confidence interva
 (norm 1) is invariant to the LLR scale, so the reference's estimated sigma versus the true sigma does not matter there; the 8PSK
 points use the on-device Estimator_DVBS2 like the reference run; the 16APSK point was taken with the perfect estimator."""
 import math
+import os
 
 import pytest
 
@@ -49,3 +50,20 @@ def test_fer_inside_the_reference_confidence_interval(modcod, ebn0, ref_fer, fra
     # the reference point rests on 100 frame errors (relative sigma 10 %); ours on n_fe; 3.5 sigma of the difference
     rel = math.sqrt(1.0 / 100 + 1.0 / max(1, mon["n_fe"]))
     assert abs(fer - ref_fer) <= 3.5 * rel * ref_fer, (fer, ref_fer, mon)
+
+
+def test_device_monte_carlo_driver_stops_on_the_frame_error_count():
+    """python -m dvbs2_b200.montecarlo: the SNR loop of dvbs2_tx_rx_bb on the device; -e frame errors end a point and the FER
+    lands on the reference binary's anchor (QPSK-S_8/9 NMS-10 at 4.0 dB: 1.52e-2 over 13 472 frames)."""
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, "-m", "dvbs2_b200.montecarlo", "--mod-cod", "QPSK-S_8/9", "--dec-implem", "NMS",
+                        "--dec-ite", "10", "-m", "4.0", "-M", "4.05", "-e", "600", "-F", "8192"], capture_output=True, text=True,
+                       timeout=600, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout + r.stderr
+    row = [ln for ln in r.stdout.splitlines() if ln.strip() and not ln.startswith("#")][-1]
+    f = [x.strip() for x in row.replace("||", "|").split("|")]
+    fra, fe, fer = int(f[2]), int(f[4]), float(f[6])
+    assert fe >= 600 and fra % 8192 == 0 and fe - 600 < 8192 * 0.05  # stopped at the first batch that crossed -e
+    assert abs(fer - 1.52e-2) < 4 * (1.52e-2 * (1 - 1.52e-2) * (1 / fra + 1 / 13472)) ** 0.5

@@ -149,8 +149,8 @@ def test_ldpc_256_frames_per_modcod_vs_reference_outputs(oracle, modcod):
         h.close()
         return V, cwd, nit
 
-    for nf, coop in ((1, 0), (1, -1), (2, -1)):
-        V, cwd, nit = run(d["llr"], "f32", ldpc_frames_per_lane=nf, ldpc_coop_max_frames=coop)
+    for nf, coop, onchip in ((1, 0, -1), (1, -1, -1), (2, -1, -1), (0, 0, 1)):  # the last: the on-chip kernel (design B)
+        V, cwd, nit = run(d["llr"], "f32", ldpc_frames_per_lane=nf, ldpc_coop_max_frames=coop, ldpc_onchip=onchip)
         assert np.array_equal(cwd, g["seq_f32_cwd"]) and np.array_equal(V, want["seq_f32"]) and np.array_equal(nit, g["seq_f32_nit"])
         for key in ("onms_f32", "tint_f32"):
             ok = g[key + "_cwd"] == 1

@@ -22,11 +22,15 @@ def _decode(modcod, Y, prec="f32", n_ite=10, norm=1.0, early_stop=True, compacti
     """Float calls run three times unless the caller pins it: through the cooperative small-batch kernel (what the library
     picks at these sizes), through the lane = frame kernel with 32-frame groups, and with 64-frame groups (the large-batch
     shape); all must give the same bits, CWD and iteration counts."""
-    if prec == "f32" and "ldpc_frames_per_lane" not in cfg:
+    if prec == "f32" and "ldpc_frames_per_lane" not in cfg and "ldpc_onchip" not in cfg:
         a = _decode(modcod, Y, prec, n_ite, norm, early_stop, compaction, ldpc_frames_per_lane=1, **cfg)
         b = _decode(modcod, Y, prec, n_ite, norm, early_stop, compaction, ldpc_frames_per_lane=1, ldpc_coop_max_frames=-1, **cfg)
         c = _decode(modcod, Y, prec, n_ite, norm, early_stop, compaction, ldpc_frames_per_lane=2, **cfg)
+        d = _decode(modcod, Y, prec, n_ite, norm, early_stop, compaction, ldpc_onchip=1, **cfg)  # design B: variables on chip
         assert all(np.array_equal(x, y) for x, y in zip(a[:3], c[:3])) and all(np.array_equal(x, y) for x, y in zip(b[:3], c[:3]))
+        assert all(np.array_equal(x, y) for x, y in zip(d[:3], c[:3]))
+        for k in ("frames", "ldpc_iterations", "ldpc_failures", "iter_hist"):
+            assert d[3][k] == c[3][k], k
         return c
     from dvbs2_b200 import Decoder_LDPC_DVBS2_cuda, Handle
 

@@ -182,3 +182,41 @@ def test_four_chunk_host_path_at_scale(ref, oracle):
     h.close()
     assert np.array_equal(c1, b["cwd"][idx]) and np.array_equal(c2, b["cb"][idx]) and np.array_equal(nit, b["nit"][idx])
     assert np.array_equal(out, want[idx])
+
+
+@pytest.mark.parametrize("modcod", ["QPSK-S_8/9", "QPSK-S_3/5", "16APSK-S_8/9"])
+def test_onchip_kernel_1e4_frames_and_bench_scale_vs_compiled_reference(ref, oracle, modcod):
+    """The on-chip LDPC kernel (design B): every one of the 10 240 verified frames, then the set tiled to 233 472 frames through
+    the fused chain (thousands of frames streaming through the 148 x F slots, frames replaced the moment they converge)."""
+    import torch
+
+    from dvbs2_b200 import Decoder_chain_DVBS2_cuda, Decoder_LDPC_DVBS2_cuda, Handle
+
+    b = _base(modcod, ref, oracle)
+    mc = MODCODS[modcod]
+    K, N, Fb = mc["K_bch"], mc["N_bch"], b["Y"].shape[0]
+    h = Handle(modcod=modcod, n_frames=Fb, ldpc_onchip=1)
+    V, cwd, nit = np.zeros((Fb, N), np.int32), np.zeros(Fb, np.int8), np.zeros(Fb, np.int32)
+    Decoder_LDPC_DVBS2_cuda(h, Fb).decode_siho(b["Y"], cwd, V, nit)
+    st = h.stats()
+    h.close()
+    assert np.array_equal(cwd, b["cwd"]) and np.array_equal(nit, b["nit"]) and np.array_equal(V, b["V"])
+    assert st["kernel_launches"] == 3 and st["iter_hist"] == [int(x) for x in np.bincount(b["nit"], minlength=33)[:33]]
+    F = 233472
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(6)
+    idx = (torch.randperm(F, generator=g) % Fb).to(dev)
+    sym, cp = b["sym"][idx].contiguous(), b["cp"][idx].contiguous()
+    h = Handle(modcod=modcod, n_frames=F, ldpc_onchip=1)
+    Vc = torch.zeros((F, K), dtype=torch.int32, device=dev)
+    c1, c2 = torch.zeros(F, dtype=torch.int8, device=dev), torch.zeros(F, dtype=torch.int8, device=dev)
+    n2 = torch.zeros(F, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    Decoder_chain_DVBS2_cuda(h, F).demodulate_decode_dev(cp, sym, c1, c2, Vc, n2)
+    h.sync()
+    h.close()
+    assert torch.equal(c1, torch.from_numpy(b["cwd"]).to(dev)[idx]) and torch.equal(c2, torch.from_numpy(b["cb"]).to(dev)[idx])
+    assert torch.equal(n2, torch.from_numpy(b["nit"]).to(dev)[idx])
+    wv = torch.from_numpy(b["Vb"]).to(dev)
+    for a in range(0, F, 32768):
+        assert torch.equal(Vc[a:a + 32768], wv[idx[a:a + 32768]]), a

@@ -37,7 +37,7 @@ def test_structs_match_header_layout():
     from dvbs2_b200 import capi
 
     lib = _lib()
-    assert C.sizeof(capi.Cfg) == 16 * 4 and C.sizeof(capi.Info) == 9 * 4 and C.sizeof(capi.Stats) == (6 + 33) * 8
+    assert C.sizeof(capi.Cfg) == 19 * 4 and C.sizeof(capi.Info) == 9 * 4 and C.sizeof(capi.Stats) == (6 + 33) * 8
     assert C.sizeof(capi.Timers) == 10 * 8 and C.sizeof(capi.Monitor) == 3 * 8
     cfg = capi.Cfg()
     lib.dvbs2_cuda_default_cfg(C.byref(cfg))
@@ -147,6 +147,21 @@ def _rank_main(rank, world, port, out):
     mon = Monitor_BFER_reduction(max_fe=800)
     mon.update(local)
     t = reduce_max(0.5 + rank)
+    # the Monte-Carlo driver's stop rule: every rank runs batches until the GLOBAL frame-error count reaches max_fe
+    from dvbs2_b200.montecarlo import run_point
+
+    cum = {"n_frames": 0, "n_be": 0, "n_fe": 0}
+
+    def step(b):
+        cum["n_frames"] += 100
+        cum["n_be"] += 10
+        cum["n_fe"] += 3 if rank == 0 else 1  # 4 frame errors per batch over both ranks
+        return dict(cum)
+
+    red, n_batches = run_point(step, max_fe=20)
+    assert n_batches == 5 and red.total == {"n_frames": 1000, "n_be": 100, "n_fe": 20}, (n_batches, red.total)
+    red, n_batches = run_point(step, max_fe=10 ** 9, max_frames=2500)
+    assert red.total["n_frames"] >= 2500 and red.is_done()
     out.put((rank, tot, mon.is_done(), mon.rates(10), t))
     dist.destroy_process_group()
 
