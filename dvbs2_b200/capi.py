@@ -16,6 +16,8 @@ IQ_FORMAT = {"f32": 0, "f16": 1, "sc16": 2, "sc8": 3}  # dvbs2_iq_format
 MODCOD = {"QPSK-S_8/9": 0, "QPSK-S_3/5": 1, "8PSK-S_3/5": 2, "8PSK-S_8/9": 3, "16APSK-S_8/9": 4}
 
 # every symbol include/dvbs2_cuda.h declares (tests check the library exports all of them)
+ABI_VERSION = 2  # DVBS2_CUDA_ABI_VERSION of include/dvbs2_cuda.h
+
 SYMBOLS = [
     "dvbs2_cuda_default_cfg", "dvbs2_cuda_create", "dvbs2_cuda_destroy", "dvbs2_cuda_get_info", "dvbs2_cuda_get_stats",
     "dvbs2_cuda_reset_stats", "dvbs2_cuda_strerror", "dvbs2_cuda_last_error", "dvbs2_cuda_device_count",
@@ -28,6 +30,7 @@ SYMBOLS = [
     "dvbs2_cuda_pl_frame_size", "dvbs2_cuda_remove_plh", "dvbs2_cuda_remove_plh_dev", "dvbs2_cuda_estimate",
     "dvbs2_cuda_estimate_dev", "dvbs2_cuda_rx_chain", "dvbs2_cuda_rx_chain_dev", "dvbs2_cuda_iq_frame_bytes",
     "dvbs2_cuda_chain_compact", "dvbs2_cuda_chain_compact_dev", "dvbs2_cuda_decode_llr8", "dvbs2_cuda_decode_llr8_dev",
+    "dvbs2_cuda_abi_version", "dvbs2_cuda_abi_check",
 ]
 
 
@@ -36,8 +39,8 @@ class Cfg(C.Structure):
                 ("early_stop", C.c_int), ("max_frames", C.c_int), ("device", C.c_int), ("quant_bits", C.c_int),
                 ("quant_dec", C.c_int), ("no_compaction", C.c_int), ("compaction_rounds", C.c_int),
                 ("compaction_exit_eighths", C.c_int), ("compaction_nf_later", C.c_int), ("ldpc_frames_per_lane", C.c_int),
-                ("ldpc_coop_max_frames", C.c_int), ("ldpc_onchip", C.c_int), ("host_pipeline_chunks", C.c_int),
-                ("reserved", C.c_int * 2)]
+                ("ldpc_coop_max_frames", C.c_int), ("host_pipeline_chunks", C.c_int), ("ldpc_onchip", C.c_int),
+                ("reserved", C.c_int * 1)]
 
 
 class Info(C.Structure):
@@ -92,6 +95,8 @@ def load():
     L.dvbs2_cuda_last_error.argtypes = [vp]
     L.dvbs2_cuda_last_error.restype = C.c_char_p
     L.dvbs2_cuda_device_count.argtypes = []
+    L.dvbs2_cuda_abi_version.argtypes = []
+    L.dvbs2_cuda_abi_check.argtypes = [ip, C.c_size_t, C.c_size_t]
     L.dvbs2_cuda_demodulate.argtypes = [vp, vp, vp, vp, ip]
     L.dvbs2_cuda_deinterleave.argtypes = [vp, vp, vp, ip]
     L.dvbs2_cuda_ldpc_decode_siho.argtypes = [vp, vp, vp, vp, vp, ip]
@@ -128,6 +133,10 @@ def load():
     L.dvbs2_cuda_tx_get_bits.argtypes = [vp, ip, vp, ip]
     L.dvbs2_cuda_monitor_check.argtypes = [vp, ip]
     L.dvbs2_cuda_monitor_get.argtypes = [vp, C.POINTER(Monitor)]
+    # the ctypes mirrors above must have the library's struct layout (a stale .so next to newer Python, or the reverse)
+    if L.dvbs2_cuda_abi_check(ABI_VERSION, C.sizeof(Cfg), C.sizeof(Stats)) != 0:
+        raise RuntimeError(LIB_PATH + " has ABI version %d, dvbs2_b200/capi.py mirrors version %d: rebuild the library"
+                           % (L.dvbs2_cuda_abi_version(), ABI_VERSION))
     _lib = L
     return L
 

@@ -652,6 +652,17 @@ extern "C"
         return n;
     }
 
+    int dvbs2_cuda_abi_version(void) { return DVBS2_CUDA_ABI_VERSION; }
+
+    int dvbs2_cuda_abi_check(int caller_version, size_t sizeof_cfg, size_t sizeof_stats)
+    {
+        static_assert(sizeof(dvbs2_cuda_cfg) == 18 * sizeof(int), "dvbs2_cuda_cfg changed size: bump DVBS2_CUDA_ABI_VERSION");
+        static_assert(sizeof(dvbs2_cuda_stats) == (6 + 33) * sizeof(uint64_t), "dvbs2_cuda_stats changed size: bump DVBS2_CUDA_ABI_VERSION");
+        return (caller_version == DVBS2_CUDA_ABI_VERSION && sizeof_cfg == sizeof(dvbs2_cuda_cfg) && sizeof_stats == sizeof(dvbs2_cuda_stats))
+                 ? DVBS2_OK
+                 : DVBS2_ERR_INVALID;
+    }
+
     const char* dvbs2_cuda_strerror(int status)
     {
         switch (status)
@@ -713,7 +724,7 @@ extern "C"
         if (cfg->host_pipeline_chunks < 0 || cfg->host_pipeline_chunks > N_PIPE) return DVBS2_ERR_INVALID;
         if (cfg->ldpc_onchip < -1 || cfg->ldpc_onchip > 1 || (cfg->ldpc_onchip == 1 && cfg->precision != DVBS2_PREC_F32))
             return DVBS2_ERR_INVALID;
-        if (cfg->reserved[0] || cfg->reserved[1]) return DVBS2_ERR_INVALID;
+        if (cfg->reserved[0]) return DVBS2_ERR_INVALID;
         if (cfg->ldpc_frames_per_lane != 0 &&
             (cfg->precision != DVBS2_PREC_F32 || (cfg->ldpc_frames_per_lane != 1 && cfg->ldpc_frames_per_lane != 2)))
             return DVBS2_ERR_INVALID;

@@ -347,10 +347,13 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
                     }
                     if (more) load_state(c + 1);
 
-                    uint32_t ns0[NP], ns1[NP];
+                    uint32_t ns0[NP], ns1[NP], nc1[NP], nc2[NP];
 #pragma unroll
                     for (int p = 0; p < NP; p++)
+                    {
                         ns0[p] = ns1[p] = 0;
+                        nc1[p] = pk::neg(c1[p]), nc2[p] = pk::neg(c2[p]);
+                    }
 #pragma unroll
                     for (int i = 0; i < D; i++)
                     {
@@ -364,10 +367,10 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
                             // edge with |t| == min1 gets the same value, as Update_rule_MS.hxx:82-92 demands)
                             const uint32_t em = pk::bitmask(i < 16 ? F0[p] : F1[p], b);
                             const uint32_t xs = sacc[p] ^ ti; // bits 15 / 31: sign of the new message
-                            const uint32_t sm = pk::signmask(xs), s1 = sm & ONE;
-                            // t + sign * mag with -mag = (mag ^ 0xffff) + 1 per half
-                            nv[p] = pk::add(pk::add(ti, pk::mux(c1[p], c2[p], em) ^ sm), s1);
-                            const uint32_t sb = s1 << b;
+                            const uint32_t sm = pk::signmask(xs);
+                            // t + sign * mag: the signed magnitude is picked from {c1, c2, -c1, -c2} with three bitwise selects
+                            nv[p] = pk::add(ti, pk::mux(pk::mux(nc1[p], c1[p], sm), pk::mux(nc2[p], c2[p], sm), em));
+                            const uint32_t sb = sm & (ONE << b); // one LOP3 with the accumulation below
                             if (i < 16)
                                 ns0[p] |= sb;
                             else

@@ -57,6 +57,9 @@ class Cuda_handle
       , h_(nullptr)
       , pin_enabled_(std::getenv("DVBS2_CUDA_NO_PIN") == nullptr)
     {
+        if (dvbs2_cuda_abi_check(DVBS2_CUDA_ABI_VERSION, sizeof(dvbs2_cuda_cfg), sizeof(dvbs2_cuda_stats)) != DVBS2_OK)
+            throw spu::tools::runtime_error(__FILE__, __LINE__, __func__,
+                                            "libdvbs2_cuda: this module was built against another version of dvbs2_cuda.h; rebuild it.");
         if (cfg_.device < 0) cfg_.device = next_device();
         const int rc = dvbs2_cuda_create(&cfg_, &h_);
         if (rc != DVBS2_OK)

@@ -360,6 +360,13 @@ main(int argc, char** argv)
         spu::runtime::Sequence seq(src("generate"), 2);
         seq.exec([&]() { return pool->next.load() >= n_batches + 2; });
         expect(cnt->frames.load() == P, "Sequence over 2 clones processed every pool frame exactly once");
+        // in-process multi-GPU: the clones StreamPU made (Sequence.cpp:1506-1535) sit on consecutive devices (Cuda_handle
+        // hands devices out round-robin when the module was built with device -1)
+        int seq_devices = 0; // bit d set: a clone of the fused stage runs on device d
+        for (auto* m : seq.get_cloned_modules<dvbs2_b200::Decoder_chain_DVBS2_cuda>(chain))
+            seq_devices |= 1 << m->get_handle().cfg().device;
+        if (dvbs2_cuda_device_count() >= 2)
+            expect(__builtin_popcount(seq_devices) == 2, "the two clones of the Sequence run on two different GPUs");
         expect(cnt->be.load() == ref_be && cnt->fe.load() == ref_fe,
                "fused GPU module in a 2-thread Sequence: BE/FE equal the reference decoders' on the same LLRs");
         expect(cnt->fe.load() == cpu_fe || std::labs(cnt->fe.load() - cpu_fe) <= 1 + cpu_fe / 10,
@@ -476,10 +483,10 @@ main(int argc, char** argv)
         printf("{\"modcod\": \"%s\", \"frames\": %d, \"demod_max_rel_err\": %.3g, \"ldpc_fe_cpu\": %d, \"bch_fe_cpu\": %ld, "
                "\"seq_frames\": %ld, \"seq_be\": %ld, \"seq_fe\": %ld, \"ref_be\": %ld, \"ref_fe\": %ld, \"cpu_be\": %ld, \"cpu_fe\": %ld, "
                "\"rx_stage_sigma_rel\": %.3g, \"rx_stage_fe\": %ld, \"rx_stage_fe_cpu\": %ld, \"compact_frames\": %ld, \"compact_fe\": %ld, "
-               "\"pinned_sockets\": %zu, \"failures\": %d}\n",
+               "\"pinned_sockets\": %zu, \"gpus\": %d, \"seq_device_mask\": %d, \"failures\": %d}\n",
                modcod.c_str(), P, max_rel, (int)std::count(c_seq.begin(), c_seq.end(), 0), cpu_fe, cnt->frames.load(),
                cnt->be.load(), cnt->fe.load(), ref_be, ref_fe, cpu_be, cpu_fe, sig_rel, rx_fe, rxc_fe, cq_frames, cq_fe, n_pinned,
-               failures);
+               dvbs2_cuda_device_count(), seq_devices, failures);
     }
     catch (const std::exception& e)
     {

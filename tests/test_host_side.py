@@ -37,7 +37,7 @@ def test_structs_match_header_layout():
     from dvbs2_b200 import capi
 
     lib = _lib()
-    assert C.sizeof(capi.Cfg) == 19 * 4 and C.sizeof(capi.Info) == 9 * 4 and C.sizeof(capi.Stats) == (6 + 33) * 8
+    assert C.sizeof(capi.Cfg) == 18 * 4 and C.sizeof(capi.Info) == 9 * 4 and C.sizeof(capi.Stats) == (6 + 33) * 8
     assert C.sizeof(capi.Timers) == 10 * 8 and C.sizeof(capi.Monitor) == 3 * 8
     cfg = capi.Cfg()
     lib.dvbs2_cuda_default_cfg(C.byref(cfg))
@@ -45,6 +45,12 @@ def test_structs_match_header_layout():
     assert (cfg.quant_bits, cfg.quant_dec) == (6, 2)  # AFF3CT's LDPC quantiser defaults (Launcher/Code/LDPC/LDPC.cpp:58-62)
     assert lib.dvbs2_cuda_strerror(0) == b"success" and b"CUDA" in lib.dvbs2_cuda_strerror(-2)
     assert lib.dvbs2_cuda_strerror(-3) and lib.dvbs2_cuda_strerror(-99) == b"unknown status"
+    # layout version: a caller built against another header is refused instead of corrupting memory
+    hdr = open(os.path.join(ROOT, "include", "dvbs2_cuda.h")).read()
+    assert int(re.search(r"#define DVBS2_CUDA_ABI_VERSION (\d+)", hdr).group(1)) == capi.ABI_VERSION == lib.dvbs2_cuda_abi_version()
+    assert lib.dvbs2_cuda_abi_check(capi.ABI_VERSION, C.sizeof(capi.Cfg), C.sizeof(capi.Stats)) == 0
+    assert lib.dvbs2_cuda_abi_check(capi.ABI_VERSION - 1, C.sizeof(capi.Cfg), C.sizeof(capi.Stats)) == -1
+    assert lib.dvbs2_cuda_abi_check(capi.ABI_VERSION, C.sizeof(capi.Cfg) + 4, C.sizeof(capi.Stats)) == -1
 
 
 def test_argument_validation_needs_no_gpu():
