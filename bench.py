@@ -228,6 +228,12 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    T0 = time.time()
+    phases = {}  # wall-clock seconds of each part of this run (reported as "wall_s": how long the default command takes)
+
+    def lap(name, since):
+        phases[name] = round(phases.get(name, 0.0) + time.time() - since, 1)
+        return time.time()
 
     import numpy as np
     import torch
@@ -314,6 +320,7 @@ def main():
         chain.demodulate_decode_dev(sig, rx, c1, c2, V, nit)
 
     torch.cuda.synchronize()
+    tp = lap("setup_and_tx", T0)
     for i in range(args.warmup):
         step(i)
     h.sync()
@@ -354,6 +361,7 @@ def main():
     mon = tx.monitor()
     mon = reduce_([mon["n_frames"], mon["n_be"], mon["n_fe"]], dist.ReduceOp.SUM if world > 1 else None)
 
+    tp = lap("warmup_timed_scoring", tp)
     # ---- roofline of the dominant kernel (LDPC decode), live CUDA-event time per launch
     peak, peak_src = hbm_peak()
     ldpc_ms = tm["ldpc_ms"] / max(1, tm["ldpc_calls"])
@@ -521,6 +529,7 @@ def main():
             if "f32_int32" in socks:
                 e2e["matches_device_path"] = socks["f32_int32"].get("matches_device_path")
 
+    tp = lap("e2e", tp)
     # ---- CPU baseline beside it (rank 0, N=1 only): the compiled reference on this box's host cores, bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -538,6 +547,7 @@ def main():
     # ---- the same workload through the fixed-point (int16, bit-exact vs AFF3CT's int16 decoder) kernel, device-resident only:
     # a separate process after this one released its HBM (N = 1 runs only; the headline stays the float path the dvbs2
     # binaries run)
+    tp = lap("cpu_baseline", tp)
     int16, configs = None, None
     if rank == 0 and world == 1 and args.prec == "f32" and (not args.no_int16 or not args.no_configs):
         if h is not None:
@@ -571,6 +581,7 @@ def main():
                 int16["e2e"] = d.get("e2e")
             except Exception as e:  # noqa: BLE001
                 int16 = {"value": None, "error": repr(e)[:300]}
+            tp = lap("int16_line", tp)
         if not args.no_configs and args.workload == "qpsk89":
             # BASELINE.json configs 2-4, device-resident: QPSK-S_3/5 at the waterfall (all iterations active), 8PSK-S_3/5 float and
             # fixed point, 8PSK-S_8/9 at high Eb/N0 (divergent iteration counts)
@@ -581,8 +592,10 @@ def main():
                     configs[name] = brief(sub(wl_, prec, ["--no-e2e"]))
                 except Exception as e:  # noqa: BLE001
                     configs[name] = {"value": None, "error": repr(e)[:300]}
+            tp = lap("configs", tp)
 
     if rank == 0:
+        phases["total"] = round(time.time() - T0, 1)
         out = {
             "metric": "info Mbit/s, %s NMS %d-iter decode chain (demap+LDPC+BCH)" % (modcod, args.ite),
             "value": round(value, 2), "unit": "Mbit/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -593,7 +606,7 @@ def main():
                        "l2": "inputs %.1f GB per step >> 126 MB L2, %d batches rotated" % (F * 2 * n_sym * 4 / 1e9, NB),
                        "parallelism": "frames sharded by batch, %d rank(s), no data-path collective" % world},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "stage_ms": stage_ms, "int16": int16, "configs": configs, "iter_hist": st["iter_hist"][:args.ite + 1],
+            "stage_ms": stage_ms, "int16": int16, "configs": configs, "wall_s": phases, "iter_hist": st["iter_hist"][:args.ite + 1],
             "fer": {"frames": int(cnt[0]), "ldpc_fer": cnt[2] / max(1, cnt[0]), "bch_fer": cnt[3] / max(1, cnt[0]),
                     "mean_iterations": cnt[1] / max(1, cnt[0]),
                     "monitor": {"frames": int(mon[0]), "bit_errors": int(mon[1]), "frame_errors": int(mon[2]),

@@ -256,12 +256,15 @@ class Decoder_chain_compact_DVBS2_cuda : public spu::module::Stateful
                                                         nullptr, static_cast<int8_t*>(t[ps_CWD1].get_dataptr()), cwd, nullptr,
                                                         static_cast<uint8_t*>(t[ps_V_K].get_dataptr()), c.descramble ? 1 : 0,
                                                         nullptr, 0, n));
+              c.handle->stage_timers(t);
               int status = 0;
               for (int f = 0; f < n; f++)
                   status |= !cwd[f];
               (void)frame_id;
               return status;
           });
+        for (const char* key : { "demap", "ldpc", "bch", "unpack" }) // device time per stage (Cuda_handle::stage_timers)
+            this->register_timer(p, key);
         this->set_single_wave(true);
         this->set_n_frames(n_frames);
         for (auto& t : this->tasks)

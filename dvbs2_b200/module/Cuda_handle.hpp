@@ -11,6 +11,7 @@
 #define DVBS2_B200_CUDA_HANDLE_HPP_
 
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <map>
 #include <sstream>
@@ -42,6 +43,8 @@ class Cuda_handle
     dvbs2_cuda_info info_;
     std::map<const void*, size_t> pinned_; // socket buffers registered by this handle (0 bytes: registration refused, not retried)
     bool pin_enabled_;
+    bool profiling_ = false;
+    dvbs2_cuda_timers timers_{};
 
     static int next_device()
     {
@@ -108,6 +111,38 @@ class Cuda_handle
         for (auto& kv : pinned_)
             n += kv.second != 0;
         return n;
+    }
+
+    /*!
+     * Per-stage device times as sub-timers of a task, like the "load / decode / store" timers of the CPU decoders
+     * (lib/aff3ct/include/Module/Decoder/Decoder_SIHO.hxx:76-79): a module registers "demap", "ldpc", "bch", "unpack" (in this
+     * order) after creating its codelet and calls stage_timers() once per codelet run.  While the task collects statistics
+     * (--sim-stats, Task::set_stats) the library records CUDA events at the stage boundaries on the launching stream
+     * (dvbs2_cuda_set_profiling); the time since the previous call goes to Task::update_timer, so the stage split of the GPU
+     * task shows up in StreamPU's statistics table.  Costs nothing when statistics are off.
+     */
+    void stage_timers(spu::runtime::Task& t)
+    {
+        if (!t.is_stats())
+        {
+            if (profiling_) dvbs2_cuda_set_profiling(h_, 0), profiling_ = false;
+            return;
+        }
+        if (!profiling_)
+        { // first call with statistics on: this call was not timed, start with the next one
+            dvbs2_cuda_set_profiling(h_, 1);
+            dvbs2_cuda_get_timers(h_, &timers_);
+            profiling_ = true;
+            return;
+        }
+        dvbs2_cuda_timers now;
+        if (dvbs2_cuda_get_timers(h_, &now) != DVBS2_OK) return;
+        const double d[4] = { now.demap_ms - timers_.demap_ms, now.ldpc_ms - timers_.ldpc_ms, now.bch_ms - timers_.bch_ms,
+                              (now.unpack_ms - timers_.unpack_ms) + (now.pack_ms - timers_.pack_ms) };
+        timers_ = now;
+        if (t.get_timers_name().size() >= 4)
+            for (size_t i = 0; i < 4; i++)
+                t.update_timer(i, std::chrono::nanoseconds((long long)(d[i] * 1e6)));
     }
 
     dvbs2_cuda_handle* get() const { return h_; }

@@ -95,12 +95,15 @@ class Decoder_chain_DVBS2_cuda : public spu::module::Stateful
                                                 static_cast<float*>(t[ps_Y_N1].get_dataptr()),
                                                 static_cast<int8_t*>(t[ps_CWD1].get_dataptr()), cwd,
                                                 static_cast<int32_t*>(t[ps_V_K].get_dataptr()), nullptr, n));
+              c.handle->stage_timers(t);
               int status = 0;
               for (int f = 0; f < n; f++)
                   status |= !cwd[f];
               (void)frame_id;
               return status;
           });
+        for (const char* key : { "demap", "ldpc", "bch", "unpack" }) // device time per stage (Cuda_handle::stage_timers)
+            this->register_timer(p, key);
         this->set_single_wave(true);
         this->set_n_frames(n_frames);
         for (auto& t : this->tasks)

@@ -69,6 +69,9 @@ def test_dvbs2_tx_rx_bb_gpu_binary_matches_cpu_binary_fer():
                                                                    "--sim-threads", str(min(4, THREADS)), "-e", "400", "--sim-stats"])
         g = _report(out)
         res[sockets] = dict(g, stage_mbps=_task_rate(out, "demodulate_decode"))
+        # the GPU task's sub-timers (device time per stage, Cuda_handle::stage_timers) are rows of the --sim-stats table
+        for key in ("demap", "ldpc", "bch", "unpack"):
+            assert re.search(r"\|\s+%s \|\|" % key, out), (key, out[-2500:])
         # same channel model, independent noise: the two FER estimates must agree within 4 sigma of their binomial spread
         p = (cpu["fe"] + g["fe"]) / (cpu["fra"] + g["fra"])
         sd = math.sqrt(p * (1 - p) * (1 / cpu["fra"] + 1 / g["fra"]))
