@@ -711,6 +711,18 @@ constexpr int COOP_WARPS = COOP_WORKERS + 1;
 // 3 * COOP_WORKERS may share an information variable.  The DVB-S2 short-frame tables give 55 (rate 8/9) and 52 (rate 3/5);
 // dvbs2_cuda_create turns the cooperative kernel off for a table that does not satisfy this (ldpc_coop_min_reuse()).
 constexpr int COOP_MIN_REUSE = 3 * COOP_WORKERS;
+// Ordering of the slot words (what compute-sanitizer's racecheck cannot see, profiles/r2_racecheck.log): per worker u there is
+// one single-count mbarrier per direction.
+//   post:    every lane of worker u writes sl[0..4]; __syncwarp(); lane 0: mbarrier.arrive.release.cta(posted[u])
+//            chain warp: mbarrier.try_wait.parity.acquire.cta(posted[u], n-th phase) -> reads sl[0..4]               (RAW ordered)
+//   answer:  every lane of the chain warp writes sl[5..9]; __syncwarp(); lane 0: arrive.release(answered[u])
+//            worker u: try_wait.acquire(answered[u], n-th phase) -> reads sl[5..9]                                   (RAW ordered)
+//   reuse:   worker u writes the post of its NEXT check only after it has read the answer to the current one, and the chain
+//            warp read that check's post before it answered; the chain warp writes the next answer for u only after fetching
+//            u's next post, which u made after reading the previous answer                                            (WAR ordered)
+// __syncwarp() orders the lanes' stores before lane 0's release (bar.warp.sync is a morally-strong synchronisation, release
+// is cumulative), so one arrival per warp suffices.  Phase parity: the n-th completion of a single-count barrier is awaited with
+// parity n & 1, and a waiter never runs more than one phase ahead of the arriver (it consumed phase n - 1 before).
 
 __device__ __forceinline__ void
 mbar_init(uint64_t* bar, unsigned count)
