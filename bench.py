@@ -53,7 +53,7 @@ def parse():
     p.add_argument("--ite", type=int, default=10)
     p.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the largest of 3, 2, 1 waves of the LDPC kernel = SMs x 12 warps x 64 frames each that fits in 80 %% of the free HBM)")
     p.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e call of one module clone (default: one wave of the LDPC kernel)")
-    p.add_argument("--e2e-clones", type=int, default=3)
+    p.add_argument("--e2e-clones", type=int, default=4, help="module clones (handles + host threads) of the e2e run; 4 keeps the GPU busiest (3: 0.80-0.83 of the device-resident rate, 4-5: 0.85, 6 does not fit in HBM)")
     p.add_argument("--e2e-chunks", type=int, default=-1, help="host_pipeline_chunks of the e2e clones (-1: 1 when there are several clones, else automatic)")
     p.add_argument("--e2e-sockets", default="", help="comma list of socket formats to time (default: f32_int32,f32_packed,sc16_packed,sc8_packed; llr8_packed with --prec i16)")
     p.add_argument("--no-configs", action="store_true", help="skip the extra lines for BASELINE configs 2-4")
@@ -417,14 +417,15 @@ def main():
             # the kernels of the others, so calls are not chunked).  The reference's int32-per-bit sockets need 14 GB of pinned
             # memory per wave and clone: half a wave there when eight ranks share one host.
             Fe = args.e2e_frames if args.e2e_frames > 0 else (wave // 2 if (fmt == "f32_int32" and world > 1) else wave)
-            Fe = max(256, min(F // NC, Fe) // 256 * 256)
+            Fe = max(256, min(F if args.e2e_frames > 0 else F // NC, Fe) // 256 * 256)
             prec = "i16" if in_kind == "llr8" else args.prec
             chunks = args.e2e_chunks if args.e2e_chunks >= 0 else (1 if NC > 1 else 0)
             clones, same = [], None
             for c in range(NC):
                 hc = Handle(modcod=modcod, n_ite=args.ite, norm=1.0, precision=prec, early_stop=True, n_frames=Fe, device=local,
                             host_pipeline_chunks=chunks, **tune)
-                src_sig, src_rx = batches[0][0][c * Fe:(c + 1) * Fe], batches[0][1][c * Fe:(c + 1) * Fe]
+                o = (c * Fe) % max(1, F - Fe + 1)  # clones take disjoint slices of batch 0 while they fit (always, by default)
+                src_sig, src_rx = batches[0][0][o:o + Fe], batches[0][1][o:o + Fe]
                 hs = pin(Fe, dtype=torch.float32)
                 hs.copy_(src_sig)
                 hc1, hc2, hn = pin(Fe, dtype=torch.int8), pin(Fe, dtype=torch.int8), pin(Fe, dtype=torch.int32)
@@ -464,14 +465,21 @@ def main():
             torch.cuda.synchronize()
 
             def run_clones(n):
+                errors = []
+
                 def work(c):
-                    for _ in range(n):
-                        clones[c][1]()
+                    try:
+                        for _ in range(n):
+                            clones[c][1]()
+                    except BaseException as e:  # noqa: BLE001 — a clone that stopped early must void the whole measurement
+                        errors.append(e)
                 ths = [threading.Thread(target=work, args=(c,)) for c in range(NC)]
                 for t in ths:
                     t.start()
                 for t in ths:
                     t.join()
+                if errors:
+                    raise errors[0]
 
             run_clones(max(1, min(args.warmup, 2)))
             for hc, _, _, _ in clones:
@@ -487,7 +495,7 @@ def main():
             n_launch = sum(hc.stats()["kernel_launches"] for hc, _, _, _ in clones)
             fails = sum(int((a["c2"] == 0).sum()) for _, _, a, _ in clones)
             if fmt == "f32_int32":  # the host result of clone 0 equals the device-resident result of the same frames
-                same = bool(np.array_equal(clones[0][2]["V"], V_head[:Fe]))
+                same = bool(np.array_equal(clones[0][2]["V"][:len(V_head)], V_head[:Fe]))
             in_b = clones[0][2]["x"].nbytes + clones[0][2]["sig"].nbytes
             out_b = clones[0][2]["V"].nbytes + 2 * Fe + 4 * Fe
             for hc, _, _, _ in clones:
