@@ -285,7 +285,9 @@ def main():
         # several waves per launch let the work queue balance groups that stop at different iterations (measured:
         # 17.4 / 18.3 / 19.2 Gbit/s at 1 / 2 / 3 waves, profiles/README.md); bounded by what fits in HBM beside the inputs
         esz0 = {"f32": 4, "i16": 2, "i8": 1}[args.prec]
-        per_frame = 1.6 * (N_LDPC * esz0 + (N_LDPC - N_bch) * (8 if args.prec == "i16" else 16) + N_LDPC // 4) + NB * (2 * n_sym * 4 + 4) + K_bch * 4 + 16
+        # decoder state incl. the compaction regions (laid out for a hand-over threshold of 6/8 float, 7/8 int16) and the later rounds' slots
+        state = {"f32": 1.85, "i16": 2.1, "i8": 1.6}[args.prec]
+        per_frame = state * (N_LDPC * esz0 + (N_LDPC - N_bch) * (8 if args.prec == "i16" else 16) + N_LDPC // 4) + NB * (2 * n_sym * 4 + 4) + K_bch * 4 + 16
         free_b = torch.cuda.mem_get_info(dev)[0]
         F = next((k * wave for k in (3, 2) if k * wave * per_frame < 0.8 * free_b), wave)
         if world > 1:  # every rank decodes the same number of frames per step (weak scaling): agree on the smallest
@@ -418,6 +420,21 @@ def main():
             # memory per wave and clone: half a wave there when eight ranks share one host.
             Fe = args.e2e_frames if args.e2e_frames > 0 else (wave // 2 if (fmt == "f32_int32" and world > 1) else wave)
             Fe = max(256, min(F if args.e2e_frames > 0 else F // NC, Fe) // 256 * 256)
+            # page-locked host memory of all clones must fit beside everything else in this box's RAM (shared by all ranks)
+            in_kind0, out_kind0 = fmt.split("_")
+            per_frame_host = ({"f32": 8, "sc16": 4, "sc8": 2}.get(in_kind0, 0) * n_sym or N_LDPC) + (4 * K_bch if out_kind0 == "int32" else K_bch // 8) + 16
+            try:
+                import psutil
+
+                budget = 0.5 * psutil.virtual_memory().available / max(1, world)
+                if NC * Fe * per_frame_host > budget:
+                    Fe = max(8192, int(budget / (NC * per_frame_host)) // 256 * 256)
+            except ImportError:
+                pass
+            if world > 1:  # the value is computed from one Fe: every rank uses the smallest
+                t = torch.tensor([Fe], dtype=torch.int64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                Fe = int(t.item())
             prec = "i16" if in_kind == "llr8" else args.prec
             chunks = args.e2e_chunks if args.e2e_chunks >= 0 else (1 if NC > 1 else 0)
             clones, same = [], None

@@ -30,7 +30,7 @@ SYMBOLS = [
     "dvbs2_cuda_pl_frame_size", "dvbs2_cuda_remove_plh", "dvbs2_cuda_remove_plh_dev", "dvbs2_cuda_estimate",
     "dvbs2_cuda_estimate_dev", "dvbs2_cuda_rx_chain", "dvbs2_cuda_rx_chain_dev", "dvbs2_cuda_iq_frame_bytes",
     "dvbs2_cuda_chain_compact", "dvbs2_cuda_chain_compact_dev", "dvbs2_cuda_decode_llr8", "dvbs2_cuda_decode_llr8_dev",
-    "dvbs2_cuda_abi_version", "dvbs2_cuda_abi_check",
+    "dvbs2_cuda_abi_version", "dvbs2_cuda_abi_check", "dvbs2_cuda_chain_compact_async", "dvbs2_cuda_wait",
 ]
 
 
@@ -124,6 +124,8 @@ def load():
     L.dvbs2_cuda_iq_frame_bytes.argtypes = [vp, ip, ip]
     L.dvbs2_cuda_iq_frame_bytes.restype = C.c_size_t
     L.dvbs2_cuda_chain_compact.argtypes = [vp, ip, C.c_float, vp, vp, vp, vp, vp, vp, vp, ip, vp, ip, ip]
+    L.dvbs2_cuda_chain_compact_async.argtypes = [vp, ip, C.c_float, vp, vp, vp, vp, vp, vp, vp, ip, vp, ip, ip]
+    L.dvbs2_cuda_wait.argtypes = [vp]
     L.dvbs2_cuda_chain_compact_dev.argtypes = [vp, ip, C.c_float, vp, vp, vp, vp, vp, vp, vp, ip, vp, ip, ip]
     L.dvbs2_cuda_decode_llr8.argtypes = [vp, vp, vp, vp, vp, vp, ip, vp, ip]
     L.dvbs2_cuda_decode_llr8_dev.argtypes = [vp, vp, vp, vp, vp, vp, ip, vp, ip]

@@ -92,6 +92,19 @@ struct dvbs2_cuda_handle
     bool auto_rounds = false; // rounds chosen per call from the batch size (cfg.compaction_rounds == 0)
     int exit_eighths = 4; // a group hands its live frames over once fewer than exit_eighths/8 of its frames still iterate
     int nf_later = 1;     // frames per lane in rounds >= 2
+    // Adaptive schedule (all three compaction knobs of the configuration left at 0): the best (rounds, hand-over threshold,
+    // later-round width) depends on how the iteration counts of the frames spread, which the decoder learns from its own
+    // statistics.  After a call the counters {frames, iterations} are copied to page-locked host memory on the call's stream;
+    // the next call polls the event (no synchronisation) and picks its schedule from the mean iteration count of the calls
+    // completed so far: see pick_schedule().  The memory regions are laid out for the widest hand-over threshold any
+    // schedule uses (layout_eighths).
+    bool adaptive = false;
+    int layout_eighths = 4;
+    unsigned long long* stat_mirror = nullptr; // pinned: {STAT_FRAMES, STAT_LDPC_ITERS} as of the last read-back
+    cudaEvent_t stat_event = nullptr;
+    bool stat_pending = false;
+    unsigned long long seen_frames = 0, seen_iters = 0;
+    double mean_it = -1.0; // mean iterations per frame of the most recent read-back interval (-1: nothing known yet)
     // staging for the host-buffer entry points (grown on demand, never beyond max_frames)
     DevBuf in_a, out_a, sigma;
     // transmitter / monitor (allocated on first use)
@@ -305,8 +318,8 @@ size_t
 region_b_offset(const dvbs2_cuda_handle* h, int f0)
 {
     // exit_eighths = 4 (the default): n / 2 slots suffice for a chunk of n frames (n a multiple of 256), no padding
-    if (h->exit_eighths == 4) return (size_t)f0 / 2;
-    return ((size_t)f0 * h->exit_eighths / 8 + 255) / 256 * 256 + (size_t)384 * (f0 / 2048);
+    if (h->layout_eighths == 4) return (size_t)f0 / 2;
+    return ((size_t)f0 * h->layout_eighths / 8 + 255) / 256 * 256 + (size_t)384 * (f0 / 2048);
 }
 size_t
 ext_slot_offset(const dvbs2_cuda_handle* h, int f0)
@@ -314,7 +327,7 @@ ext_slot_offset(const dvbs2_cuda_handle* h, int f0)
     // n * (e + e^2 + ... + e^(MAX_ROUNDS - 1)) with e = exit_eighths / 8, rounded up, + one group of padding per round and chunk
     double sum = 0, pw = 1;
     for (int r = 2; r <= MAX_ROUNDS; r++)
-        pw *= h->exit_eighths / 8.0, sum += pw;
+        pw *= h->layout_eighths / 8.0, sum += pw;
     return ((size_t)std::ceil((double)f0 * sum) + 255) / 256 * 256 + (size_t)256 * (MAX_ROUNDS - 1) * (f0 / 2048);
 }
 
@@ -354,6 +367,50 @@ run_ldpc_onchip(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const flo
     return DVBS2_OK;
 }
 
+// The schedule of one multi-round call: decoding rounds, hand-over threshold (eighths of a group), frames per lane of the
+// later rounds.  Fixed by the configuration, or — h->adaptive — picked from what the previous calls measured:
+//   * mean iterations between 0.45 and 0.9 of the budget (frames converge at widely different iterations — the
+//     waterfall edge, e.g. QPSK-S_8/9 at 4 dB: 6.1 of 10) and a launch of at least two waves: hand over earlier and more
+//     often (4 rounds, threshold 6/8 with 64-frame later groups for float, 7/8 for int16);
+//   * otherwise (everything converges early and together — 8PSK-S_8/9 at 7.5 dB, 2.9 of 10 — or hardly anything converges
+//     — QPSK-S_3/5 at 2.2 dB, 9.7 of 10 — or nothing is known yet): 3 rounds at 4/8 from two waves on, else 2 rounds.
+// Measured on one box (profiles/r2_schedule_sweep.txt): QPSK-S_8/9 float 19.0 -> 19.75 Gbit/s, int16 28.8 -> 29.9; the same
+// schedule costs 5 % (float) / 10 % (int16) on 8PSK-S_8/9 at 7.5 dB and 2 - 4 % on QPSK-S_3/5, hence the rule.  The schedule
+// never changes a result (tests: test_multi_round_compaction_is_transparent).
+struct Schedule
+{
+    int rounds, eighths, nf_later;
+};
+
+Schedule
+pick_schedule(dvbs2_cuda_handle* h, int n_groups0)
+{
+    const bool waves2 = n_groups0 >= 2 * h->n_sms * LDPC_WARPS;
+    Schedule sc{ (h->auto_rounds && !waves2) ? 2 : h->rounds, h->exit_eighths, h->nf_later };
+    if (!h->adaptive) return sc;
+    if (h->stat_pending && cudaEventQuery(h->stat_event) == cudaSuccess)
+    {
+        h->stat_pending = false;
+        unsigned long long f = h->stat_mirror[0], it = h->stat_mirror[1];
+        if (f < h->seen_frames || it < h->seen_iters) h->seen_frames = h->seen_iters = 0; // the counters were reset in between
+        if (f - h->seen_frames >= 4096)
+        {
+            h->mean_it = (double)(it - h->seen_iters) / (double)(f - h->seen_frames);
+            h->seen_frames = f, h->seen_iters = it;
+        }
+    }
+    else
+        cudaGetLastError(); // cudaErrorNotReady is not an error
+    const double x = h->mean_it / h->cfg.n_ite;
+    if (waves2 && h->mean_it > 0 && x >= 0.45 && x <= 0.9)
+    {
+        sc.rounds = 4;
+        sc.eighths = h->layout_eighths; // 6 (float) / 7 (int16)
+        sc.nf_later = h->cfg.precision == DVBS2_PREC_F32 ? 2 : h->nf_later;
+    }
+    return sc;
+}
+
 // LDPC decode of slots [first_frame, first_frame + n_frames): one round, or several rounds with frame compaction in
 // between (at most h->rounds; a round is worth launching only while the previous one had at least two groups)
 int
@@ -383,7 +440,8 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
     const int n_groups0 = a.n_groups;
 
     // round 1 (in place), then compaction + round r for r = 2..rounds
-    a.exit_below = 32 * nf0 * h->exit_eighths / 8;
+    const Schedule sc = pick_schedule(h, n_groups0);
+    a.exit_below = 32 * nf0 * sc.eighths / 8;
     a.surv_mask = mask0;
     a.surv_iters = (int*)h->surv_iters.p + first_frame;
     CU(h, launch_ldpc_decode(a, h->cfg.precision, s));
@@ -393,10 +451,10 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
     const int* prev_n_slots = nullptr;
     // measured (profiles/README.md): a third round pays once a launch holds two or more waves of groups (the queue then
     // has work to balance); with a single wave the extra compaction and the short tail kernel cost more than they save
-    const int rounds = (h->auto_rounds && n_groups0 < 2 * h->n_sms * LDPC_WARPS) ? 2 : h->rounds;
+    const int rounds = sc.rounds;
     for (int r = 2; r <= rounds && prev.n_groups >= 2; r++)
     {
-        const int nf = std::min(nf0, ldpc_later_frames_per_lane(h->cfg.precision, h->nf_later)); // groups never widen
+        const int nf = std::min(nf0, ldpc_later_frames_per_lane(h->cfg.precision, sc.nf_later)); // groups never widen
         const int gsz = 32 * nf;
         // every group of the previous round hands over fewer than exit_below frames
         const int cap = (prev.n_groups * (prev.exit_below - 1) + gsz - 1) / gsz * gsz;
@@ -429,7 +487,7 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
         b.n_frames = cap, b.n_groups = cap / gsz, b.nf = nf;
         b.n_slots_dev = c.n_surv, b.slot_frame = c.dst_frame, b.slot_iters = c.dst_iters;
         const bool last = r == rounds || b.n_groups < 2;
-        b.exit_below = last ? 0 : gsz * h->exit_eighths / 8;
+        b.exit_below = last ? 0 : gsz * sc.eighths / 8;
         b.surv_mask = last ? nullptr : (uint32_t*)h->surv_mask.p + hs / 32;
         b.surv_iters = last ? nullptr : (int*)h->surv_iters.p + hs;
         CU(h, launch_ldpc_decode(b, h->cfg.precision, s));
@@ -440,6 +498,13 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
     MergeLaunch m{};
     m.surv_mask = mask0, m.final_loc = final_loc, m.out_hd = out_hd0, m.n_groups = n_groups0, m.nf = nf0;
     CU(h, launch_merge_back(m, s));
+    if (h->adaptive && !h->stat_pending)
+    { // what this call (and everything before it on this stream) measured, for the calls after it: no host synchronisation
+        static_assert(STAT_FRAMES == 0 && STAT_LDPC_ITERS == 1, "the read-back copies the first two counters");
+        CU(h, cudaMemcpyAsync(h->stat_mirror, h->stats.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        CU(h, cudaEventRecord(h->stat_event, s));
+        h->stat_pending = true;
+    }
     return DVBS2_OK;
 }
 
@@ -698,6 +763,8 @@ extern "C"
         if (h->stream) cudaStreamDestroy(h->stream);
         for (auto& m : h->marks)
             cudaEventDestroy(m.ev);
+        if (h->stat_event) cudaEventDestroy(h->stat_event);
+        if (h->stat_mirror) cudaFreeHost(h->stat_mirror);
         delete h;
         return DVBS2_OK;
     }
@@ -816,6 +883,15 @@ extern "C"
         h->auto_rounds = !cfg->no_compaction && cfg->compaction_rounds <= 0;
         h->exit_eighths = cfg->compaction_exit_eighths > 0 ? std::min(cfg->compaction_exit_eighths, 7) : 4;
         h->nf_later = ldpc_later_frames_per_lane(cfg->precision, cfg->compaction_nf_later);
+        h->adaptive = !cfg->no_compaction && cfg->compaction_rounds <= 0 && cfg->compaction_exit_eighths <= 0 &&
+                      cfg->compaction_nf_later <= 0 && cfg->precision != DVBS2_PREC_I8 && cfg->early_stop;
+        h->layout_eighths = !h->adaptive ? h->exit_eighths : (cfg->precision == DVBS2_PREC_F32 ? 6 : 7);
+        if (h->adaptive)
+        {
+            CUB(cudaHostAlloc((void**)&h->stat_mirror, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+            h->stat_mirror[0] = h->stat_mirror[1] = 0;
+            CUB(cudaEventCreateWithFlags(&h->stat_event, cudaEventDisableTiming));
+        }
         h->ext_cap = h->rounds > 1 ? (int)region_b_offset(h, (h->max_frames + 255) / 256 * 256) + 512 : 0;
         h->ext_slots = h->rounds > 1 ? (int)ext_slot_offset(h, (h->max_frames + 255) / 256 * 256) + 256 * MAX_ROUNDS : 0;
         const size_t FE = F + h->ext_cap;                    // var / cn slots
@@ -898,6 +974,9 @@ extern "C"
         if (!h) return DVBS2_ERR_INVALID;
         TRY(dvbs2_cuda_sync(h));
         CU(h, cudaMemset(h->stats.p, 0, h->stats.bytes));
+        h->seen_frames = h->seen_iters = 0; // the schedule statistics restart with the counters (everything queued has finished:
+        h->stat_pending = false;            // dvbs2_cuda_sync above); what was learnt so far (mean_it) stays
+        if (h->stat_mirror) h->stat_mirror[0] = h->stat_mirror[1] = 0;
         h->launches = 0;
         if (h->mon.p) CU(h, cudaMemset(h->mon.p, 0, h->mon.bytes));
         TRY(prof_collect(h));
@@ -1121,7 +1200,8 @@ extern "C"
     // (AFF3CT socket type) when packed == nullptr, else packed bytes.
     static int chain_host(dvbs2_cuda_handle* h, const float* CP, const void* Y_N1, int8_t* CWD_ldpc, int8_t* CWD_bch,
                           int32_t* V_K, uint8_t* packed, int descramble, int32_t* n_iter, int n_frames, bool pl_frames = false,
-                          float* SIG = nullptr, int iq_fmt = DVBS2_IQ_F32, float iq_scale = 1.f, bool llr8 = false)
+                          float* SIG = nullptr, int iq_fmt = DVBS2_IQ_F32, float iq_scale = 1.f, bool llr8 = false,
+                          bool wait = true)
     {
         TRY(check_frames(h, n_frames));
         if (!Y_N1 || (V_K != nullptr) == (packed != nullptr)) return DVBS2_ERR_INVALID; // exactly one output format
@@ -1165,6 +1245,7 @@ extern "C"
                 if (n_iter) CU(h, cudaMemcpyAsync(n_iter + f0, d_nit, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, s));
                 return DVBS2_OK;
             }();
+        if (rc == DVBS2_OK && !wait) return DVBS2_OK; // the *_async entry point: dvbs2_cuda_wait() collects the call
         const int rs = sync_pipes(h); // also after a failure: nothing queued may outlive the call
         return rc != DVBS2_OK ? rc : rs;
     }
@@ -1197,6 +1278,22 @@ extern "C"
         if (!CP && !pl_frames) return DVBS2_ERR_INVALID; // the estimator works on PL frames' payload; XFEC callers pass sigma
         return chain_host(h, CP, Y_N1, CWD_ldpc, CWD_bch, V_K, V_K_packed, descramble, n_iter, n_frames, pl_frames != 0, SIG,
                           iq_format, iq_scale);
+    }
+
+    int dvbs2_cuda_chain_compact_async(dvbs2_cuda_handle* h, int iq_format, float iq_scale, const float* CP, const void* Y_N1,
+                                       float* SIG, int8_t* CWD_ldpc, int8_t* CWD_bch, int32_t* V_K, uint8_t* V_K_packed,
+                                       int descramble, int32_t* n_iter, int pl_frames, int n_frames)
+    {
+        if (!CP && !pl_frames) return DVBS2_ERR_INVALID;
+        return chain_host(h, CP, Y_N1, CWD_ldpc, CWD_bch, V_K, V_K_packed, descramble, n_iter, n_frames, pl_frames != 0, SIG,
+                          iq_format, iq_scale, false, /*wait*/ false);
+    }
+
+    int dvbs2_cuda_wait(dvbs2_cuda_handle* h)
+    {
+        if (!h) return DVBS2_ERR_INVALID;
+        CU(h, cudaSetDevice(h->cfg.device));
+        return sync_pipes(h);
     }
 
     int dvbs2_cuda_chain_compact_dev(dvbs2_cuda_handle* h, int iq_format, float iq_scale, const float* d_CP,

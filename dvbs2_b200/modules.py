@@ -316,6 +316,22 @@ class Decoder_chain_compact_DVBS2_cuda(_Module):
             opt(V_K_packed, np.uint8, F * (self.K // 8), "V_K_packed"), int(bool(descramble)),
             opt(n_iter, np.int32, F, "n_iter"), int(self.pl_frames), F))
 
+    def demodulate_decode_async(self, CP, Y_N1, CWD_ldpc=None, CWD_bch=None, V_K=None, V_K_packed=None, n_iter=None,
+                                descramble=False, SIG=None):
+        """Queues the call and returns (dvbs2_cuda_chain_compact_async); wait() blocks until the results are in the host
+        buffers.  The buffers must be page-locked and stay untouched until then; one call in flight per handle."""
+        F, h = self.n_frames, self.h
+        opt = lambda a, dt, n, name: None if a is None else _np_ptr(a, dt, n, name)  # noqa: E731
+        h.check(h.lib.dvbs2_cuda_chain_compact_async(
+            h._h, capi.IQ_FORMAT[self.iq_format], self.iq_scale, opt(CP, np.float32, F, "CP"),
+            _np_ptr(Y_N1, IQ_DTYPE[self.iq_format], F * self.N_fil, "Y_N1"), opt(SIG, np.float32, F, "SIG"),
+            opt(CWD_ldpc, np.int8, F, "CWD_ldpc"), opt(CWD_bch, np.int8, F, "CWD_bch"), opt(V_K, np.int32, F * self.K, "V_K"),
+            opt(V_K_packed, np.uint8, F * (self.K // 8), "V_K_packed"), int(bool(descramble)),
+            opt(n_iter, np.int32, F, "n_iter"), int(self.pl_frames), F))
+
+    def wait(self):
+        self.h.check(self.h.lib.dvbs2_cuda_wait(self.h._h))
+
     def demodulate_decode_dev(self, CP, Y_N1, CWD_ldpc=None, CWD_bch=None, V_K=None, V_K_packed=None, n_iter=None,
                               descramble=False, SIG=None):
         F, h = self.n_frames, self.h

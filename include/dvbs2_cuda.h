@@ -86,7 +86,11 @@ extern "C"
         int no_compaction; /* 0 (default): frames still iterating when most of their group has converged are packed
                               into dense groups for the remaining iterations (same results, fewer bytes moved);
                               1: every frame stays in its group                                                  */
-        int compaction_rounds;       /* decoding rounds incl. the first, 2..6 (0 = 2, or 3 from two waves of groups on) */
+        int compaction_rounds;       /* decoding rounds incl. the first, 2..6 (0 = 2, or 3 from two waves of groups on).  With
+                                      * this and the next two fields all 0 the schedule is ADAPTIVE: the handle reads back its own
+                                      * iteration statistics after every call (no synchronisation) and, once the mean iteration
+                                      * count of the traffic lies between 0.45 and 0.9 of n_ite, large calls run 4 rounds with a
+                                      * hand-over threshold of 6/8 (float) / 7/8 (int16).  Results never depend on the schedule. */
         int compaction_exit_eighths; /* a group hands its live frames over once fewer than this many eighths of its
                                         frames still iterate, 1..7 (0 = default 4)                                   */
         int compaction_nf_later;     /* frames per lane in rounds >= 2: f32 1 or 2 (0 = 1), int16 2 or 4 (0 = 2)   */
@@ -204,6 +208,16 @@ extern "C"
     int dvbs2_cuda_chain_compact(dvbs2_cuda_handle* h, int iq_format, float iq_scale, const float* CP, const void* Y_N1,
                                  float* SIG, int8_t* CWD_ldpc, int8_t* CWD_bch, int32_t* V_K, uint8_t* V_K_packed,
                                  int descramble, int32_t* n_iter, int pl_frames, int n_frames);
+    /* Asynchronous form of dvbs2_cuda_chain_compact (host-pointer *_async entry points): queues the H2D copies,
+     * the kernels and the D2H copies of the call on the handle's pipeline streams and returns; dvbs2_cuda_wait() blocks until
+     * they have finished (and returns the first CUDA error).  The host buffers must be page-locked (dvbs2_cuda_host_register,
+     * otherwise the copies are synchronous anyway) and must stay untouched until dvbs2_cuda_wait returns; one call in flight
+     * per handle.  One host thread can thus keep several handles — several GPUs — busy: queue on each, then wait on each.
+     * A failure while queueing waits for what was already queued before it returns, like the synchronous entry points. */
+    int dvbs2_cuda_chain_compact_async(dvbs2_cuda_handle* h, int iq_format, float iq_scale, const float* CP, const void* Y_N1,
+                                       float* SIG, int8_t* CWD_ldpc, int8_t* CWD_bch, int32_t* V_K, uint8_t* V_K_packed,
+                                       int descramble, int32_t* n_iter, int pl_frames, int n_frames);
+    int dvbs2_cuda_wait(dvbs2_cuda_handle* h);
     int dvbs2_cuda_chain_compact_dev(dvbs2_cuda_handle* h, int iq_format, float iq_scale, const float* d_CP,
                                      const void* d_Y_N1, float* d_SIG, int8_t* d_CWD_ldpc, int8_t* d_CWD_bch, int32_t* d_V_K,
                                      uint8_t* d_V_K_packed, int descramble, int32_t* d_n_iter, int pl_frames, int n_frames);

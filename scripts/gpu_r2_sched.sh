@@ -22,3 +22,10 @@ for wl in qpsk89 8psk89 qpsk35; do
   run $wl r4e6n1 --rounds 4 --exit-eighths 6
 done
 run qpsk89 default2
+for wl in qpsk89 8psk89 qpsk35; do
+  run $wl i16_default --prec i16
+  run $wl i16_r4e7 --prec i16 --rounds 4 --exit-eighths 7
+  run $wl i16_r5e7 --prec i16 --rounds 5 --exit-eighths 7
+  run $wl i16_r4e6 --prec i16 --rounds 4 --exit-eighths 6
+done
+timeout 600 python -m pytest -q -m gpu -x tests/test_gpu_compact_sockets.py -k "async" 2>&1 | tail -3

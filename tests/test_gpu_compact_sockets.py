@@ -101,3 +101,47 @@ def test_int8_llr_socket_is_bit_exact_with_the_int16_decoder(oracle, modcod, ebn
     with pytest.raises(Exception):
         Decoder_llr8_DVBS2_cuda(hf, F).decode(q8, V_K=V)  # float handle: the int8 socket feeds the fixed-point decoder only
     hf.close()
+
+
+def test_async_entry_point_two_handles_one_host_thread(oracle):
+    """dvbs2_cuda_chain_compact_async + dvbs2_cuda_wait: one host thread queues a call on each of two handles (page-locked
+    buffers), then waits for both — same bytes as the synchronous entry point."""
+    import torch
+
+    from dvbs2_b200 import Decoder_chain_compact_DVBS2_cuda, Handle
+    from dvbs2_b200.modules import iq_pack
+
+    modcod, F = "QPSK-S_8/9", 2048 + 70
+    K = MODCODS[modcod]["K_bch"]
+    s = synth_frames(oracle, modcod, 70, 4.0, seed=5)
+    reps = (F + 69) // 70
+    rx = np.tile(s["rx"], (reps, 1))[:F]
+    sig = np.tile(s["sigma"], reps)[:F]
+    wire = np.ascontiguousarray(iq_pack(rx, "sc16", 1.0 / 8192))
+    h0 = Handle(modcod=modcod, n_frames=F)
+    m0 = Decoder_chain_compact_DVBS2_cuda(h0, F, "sc16", 1.0 / 8192)
+    want = np.zeros((F, K // 8), np.uint8)
+    want_c = np.zeros(F, np.int8)
+    m0.demodulate_decode(sig, wire, CWD_bch=want_c, V_K_packed=want, descramble=True)
+    h0.close()
+    assert np.array_equal(want[:70], want[70:140])  # tiled input, tiled output
+
+    def pinned(a):
+        t = torch.from_numpy(a.copy()).pin_memory()
+        return t, t.numpy()
+
+    clones = []
+    for _ in range(2):
+        h = Handle(modcod=modcod, n_frames=F, host_pipeline_chunks=2)
+        m = Decoder_chain_compact_DVBS2_cuda(h, F, "sc16", 1.0 / 8192)
+        keep = [pinned(sig), pinned(wire), pinned(np.zeros((F, K // 8), np.uint8)), pinned(np.zeros(F, np.int8))]
+        clones.append((h, m, keep))
+    for _ in range(2):  # twice: the second round reuses the device buffers of the first
+        for h, m, keep in clones:
+            keep[2][1][:] = 0
+            m.demodulate_decode_async(keep[0][1], keep[1][1], CWD_bch=keep[3][1], V_K_packed=keep[2][1], descramble=True)
+        for h, m, keep in clones:
+            m.wait()
+            assert np.array_equal(keep[2][1], want) and np.array_equal(keep[3][1], want_c)
+    for h, _, _ in clones:
+        h.close()
