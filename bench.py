@@ -287,7 +287,8 @@ def main():
         esz0 = {"f32": 4, "i16": 2, "i8": 1}[args.prec]
         # decoder state incl. the compaction regions (laid out for a hand-over threshold of 6/8 float, 7/8 int16) and the later rounds' slots
         state = {"f32": 1.85, "i16": 2.1, "i8": 1.6}[args.prec]
-        per_frame = state * (N_LDPC * esz0 + (N_LDPC - N_bch) * (8 if args.prec == "i16" else 16) + N_LDPC // 4) + NB * (2 * n_sym * 4 + 4) + K_bch * 4 + 16
+        cn_b = (12 if N_bch == 9720 else 16) // (2 if args.prec == "i16" else 1)  # compressed check state per check and frame
+        per_frame = state * (N_LDPC * esz0 + (N_LDPC - N_bch) * cn_b + N_LDPC // 4) + NB * (2 * n_sym * 4 + 4) + K_bch * 4 + 16
         free_b = torch.cuda.mem_get_info(dev)[0]
         F = next((k * wave for k in (3, 2) if k * wave * per_frame < 0.8 * free_b), wave)
         if world > 1:  # every rank decodes the same number of frames per step (weak scaling): agree on the smallest
@@ -374,7 +375,8 @@ def main():
     d_info = 25 if N_bch == 14400 else 9
     E_info = M * d_info
     it_per_frame = st["ldpc_iterations"] / max(1, st["frames"])
-    cn_rw = 16 if args.prec == "i16" else 32  # check state read + written per check and frame (packed pairs for int16)
+    # check state read + written per check and frame (packed pairs for int16; 12-byte state for the degree-11 checks of rate 3/5)
+    cn_rw = 2 * (12 if d_info == 9 else 16) // (2 if args.prec == "i16" else 1)
     msg_bytes_frame = it_per_frame * (2 * esz * E_info + 2 * esz * M + cn_rw * M)  # DESIGN.md §5 message-passing traffic
     roofline = {"bound": "hbm", "kernel": "ldpc_decode_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,

@@ -67,7 +67,9 @@ struct dvbs2_cuda_handle
     size_t elt = 4; // sizeof(R)
     int coop_max = 16384; // float calls of up to this many frames use the cooperative small-batch LDPC kernel (0 = never)
     int nf_cfg = 0; // float only: frames per lane forced by the configuration (0 = chosen per call from the batch size)
-    int cn_div = 1; // check state: 16 / cn_div bytes per frame and check (int16 packs two frames into one uint4)
+    int cn_div = 1; // check state: 4 * state_words / cn_div bytes per frame and check (int16 packs two frames into one element)
+    int state_words = 4; // ldpc_state_words(d_info): 3 for the degree-11 checks of the rate-3/5 codes
+    size_t cn_bytes = 16; // = 4 * state_words / cn_div
     cudaStream_t stream = nullptr;
     cudaStream_t pipe[N_PIPE] = {};
     // code tables
@@ -100,11 +102,12 @@ struct dvbs2_cuda_handle
     // schedule uses (layout_eighths).
     bool adaptive = false;
     int layout_eighths = 4;
-    unsigned long long* stat_mirror = nullptr; // pinned: {STAT_FRAMES, STAT_LDPC_ITERS} as of the last read-back
+    unsigned long long* stat_mirror = nullptr; // pinned: {STAT_FRAMES, STAT_LDPC_ITERS, STAT_LDPC_FAIL} as of the last read-back
     cudaEvent_t stat_event = nullptr;
     bool stat_pending = false;
-    unsigned long long seen_frames = 0, seen_iters = 0;
+    unsigned long long seen_frames = 0, seen_iters = 0, seen_fails = 0;
     double mean_it = -1.0; // mean iterations per frame of the most recent read-back interval (-1: nothing known yet)
+    double fail_frac = 0.0; // fraction of frames of that interval whose syndrome was still non-zero after the last iteration
     // staging for the host-buffer entry points (grown on demand, never beyond max_frames)
     DevBuf in_a, out_a, sigma;
     // transmitter / monitor (allocated on first use)
@@ -259,7 +262,7 @@ ldpc_args(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frames, i
 {
     LdpcLaunch a{};
     a.var = (char*)h->var.p + (size_t)first_frame * N_LDPC * h->elt;
-    a.cn = (uint4*)h->cn.p + (size_t)first_frame * h->mc.M / h->cn_div;
+    a.cn = (uint4*)((char*)h->cn.p + (size_t)first_frame * h->mc.M * h->cn_bytes);
     a.hd = (uint32_t*)h->hd.p + (size_t)(first_frame / 32) * N_LDPC;
     a.out_hd = (uint32_t*)h->out_hd.p + (size_t)(first_frame / 32) * N_LDPC;
     a.idx32 = h->d_idx32, a.last = h->d_last;
@@ -370,8 +373,9 @@ run_ldpc_onchip(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, const flo
 // The schedule of one multi-round call: decoding rounds, hand-over threshold (eighths of a group), frames per lane of the
 // later rounds.  Fixed by the configuration, or — h->adaptive — picked from what the previous calls measured:
 //   * mean iterations between 0.45 and 0.9 of the budget (frames converge at widely different iterations — the
-//     waterfall edge, e.g. QPSK-S_8/9 at 4 dB: 6.1 of 10) and a launch of at least two waves: hand over earlier and more
-//     often (4 rounds, threshold 6/8 with 64-frame later groups for float, 7/8 for int16);
+//     waterfall edge, e.g. QPSK-S_8/9 at 4 dB: 6.1 of 10), few frames that never converge (<= 20 % float, <= 8 % int16) and a
+//     launch of at least two waves: hand over earlier and more often (4 rounds, threshold 6/8 with 64-frame later groups for
+//     float, 7/8 for int16);
 //   * otherwise (everything converges early and together — 8PSK-S_8/9 at 7.5 dB, 2.9 of 10 — or hardly anything converges
 //     — QPSK-S_3/5 at 2.2 dB, 9.7 of 10 — or nothing is known yet): 3 rounds at 4/8 from two waves on, else 2 rounds.
 // Measured on one box (profiles/r2_schedule_sweep.txt): QPSK-S_8/9 float 19.0 -> 19.75 Gbit/s, int16 28.8 -> 29.9; the same
@@ -391,18 +395,23 @@ pick_schedule(dvbs2_cuda_handle* h, int n_groups0)
     if (h->stat_pending && cudaEventQuery(h->stat_event) == cudaSuccess)
     {
         h->stat_pending = false;
-        unsigned long long f = h->stat_mirror[0], it = h->stat_mirror[1];
-        if (f < h->seen_frames || it < h->seen_iters) h->seen_frames = h->seen_iters = 0; // the counters were reset in between
+        unsigned long long f = h->stat_mirror[0], it = h->stat_mirror[1], fl = h->stat_mirror[2];
+        if (f < h->seen_frames || it < h->seen_iters || fl < h->seen_fails) // the counters were reset in between
+            h->seen_frames = h->seen_iters = h->seen_fails = 0;
         if (f - h->seen_frames >= 4096)
         {
             h->mean_it = (double)(it - h->seen_iters) / (double)(f - h->seen_frames);
-            h->seen_frames = f, h->seen_iters = it;
+            h->fail_frac = (double)(fl - h->seen_fails) / (double)(f - h->seen_frames);
+            h->seen_frames = f, h->seen_iters = it, h->seen_fails = fl;
         }
     }
     else
         cudaGetLastError(); // cudaErrorNotReady is not an error
     const double x = h->mean_it / h->cfg.n_ite;
-    if (waves2 && h->mean_it > 0 && x >= 0.45 && x <= 0.9)
+    // frames that never converge are carried through every compaction: the wider the threshold, the fewer of them it tolerates
+    // (int16 with 7/8: +3.6 % at 4 % failures, -4.2 % at 13 %; float with 6/8: +4.9 % at 3 %, +3.2 % at 11 %)
+    const double max_fail = h->cfg.precision == DVBS2_PREC_F32 ? 0.2 : 0.08;
+    if (waves2 && h->mean_it > 0 && x >= 0.45 && x <= 0.9 && h->fail_frac <= max_fail)
     {
         sc.rounds = 4;
         sc.eighths = h->layout_eighths; // 6 (float) / 7 (int16)
@@ -475,7 +484,8 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
         c.final_loc = final_loc;
         c.dst_slot0 = (int)(hs - first_frame);
         c.var_src = prev.var, c.var_dst = (char*)h->var.p + vslot * N_LDPC * h->elt;
-        c.cn_src = prev.cn, c.cn_dst = (uint4*)h->cn.p + vslot * h->mc.M / h->cn_div;
+        c.cn_src = prev.cn, c.cn_dst = (uint4*)((char*)h->cn.p + vslot * h->mc.M * h->cn_bytes);
+        c.state_words = h->state_words;
         c.n_groups = prev.n_groups, c.nf = prev.nf, c.cap = cap, c.M = h->mc.M, c.nf_dst = nf;
         CU(h, launch_compact(c, h->cfg.precision, s));
 
@@ -500,8 +510,8 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
     CU(h, launch_merge_back(m, s));
     if (h->adaptive && !h->stat_pending)
     { // what this call (and everything before it on this stream) measured, for the calls after it: no host synchronisation
-        static_assert(STAT_FRAMES == 0 && STAT_LDPC_ITERS == 1, "the read-back copies the first two counters");
-        CU(h, cudaMemcpyAsync(h->stat_mirror, h->stats.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        static_assert(STAT_FRAMES == 0 && STAT_LDPC_ITERS == 1 && STAT_LDPC_FAIL == 2, "the read-back copies the first three counters");
+        CU(h, cudaMemcpyAsync(h->stat_mirror, h->stats.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         CU(h, cudaEventRecord(h->stat_event, s));
         h->stat_pending = true;
     }
@@ -808,6 +818,8 @@ extern "C"
         h->coop_max = cfg->ldpc_coop_max_frames < 0 ? 0 : cfg->ldpc_coop_max_frames > 0 ? cfg->ldpc_coop_max_frames : 16384;
         h->nf_cfg = cfg->ldpc_frames_per_lane; // float only (validated above): 1 or 2 in round 1; 0 = per call from the batch size
         h->cn_div = cfg->precision == DVBS2_PREC_I16 ? 2 : 1;
+        h->state_words = ldpc_state_words(mc.d_info);
+        h->cn_bytes = (size_t)4 * h->state_words / h->cn_div;
         h->max_frames = (cfg->max_frames + 32 * h->nf - 1) / (32 * h->nf) * (32 * h->nf);
         h->max_groups = h->max_frames / 32;
 
@@ -888,8 +900,8 @@ extern "C"
         h->layout_eighths = !h->adaptive ? h->exit_eighths : (cfg->precision == DVBS2_PREC_F32 ? 6 : 7);
         if (h->adaptive)
         {
-            CUB(cudaHostAlloc((void**)&h->stat_mirror, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
-            h->stat_mirror[0] = h->stat_mirror[1] = 0;
+            CUB(cudaHostAlloc((void**)&h->stat_mirror, 3 * sizeof(unsigned long long), cudaHostAllocDefault));
+            h->stat_mirror[0] = h->stat_mirror[1] = h->stat_mirror[2] = 0;
             CUB(cudaEventCreateWithFlags(&h->stat_event, cudaEventDisableTiming));
         }
         h->ext_cap = h->rounds > 1 ? (int)region_b_offset(h, (h->max_frames + 255) / 256 * 256) + 512 : 0;
@@ -897,7 +909,7 @@ extern "C"
         const size_t FE = F + h->ext_cap;                    // var / cn slots
         const size_t FS = F + h->ext_slots, GS = FS / 32;    // hd / out_hd / bookkeeping slots
         int rc;
-        if ((rc = ensure(h, h->var, FE * N_LDPC * h->elt)) || (rc = ensure(h, h->cn, FE * mc.M * sizeof(uint4) / h->cn_div)) ||
+        if ((rc = ensure(h, h->var, FE * N_LDPC * h->elt)) || (rc = ensure(h, h->cn, FE * mc.M * h->cn_bytes)) ||
             (rc = ensure(h, h->hd, GS * N_LDPC * 4)) || (rc = ensure(h, h->out_hd, GS * N_LDPC * 4)) ||
             (rc = ensure(h, h->surv_mask, GS * 4 + 4)) || (rc = ensure(h, h->surv_iters, FS * 4 + 4)) ||
             (rc = ensure(h, h->dst_base, GS * 4 + 4)) || (rc = ensure(h, h->src_of_dst, FS * 4 + 4)) ||
@@ -974,9 +986,9 @@ extern "C"
         if (!h) return DVBS2_ERR_INVALID;
         TRY(dvbs2_cuda_sync(h));
         CU(h, cudaMemset(h->stats.p, 0, h->stats.bytes));
-        h->seen_frames = h->seen_iters = 0; // the schedule statistics restart with the counters (everything queued has finished:
-        h->stat_pending = false;            // dvbs2_cuda_sync above); what was learnt so far (mean_it) stays
-        if (h->stat_mirror) h->stat_mirror[0] = h->stat_mirror[1] = 0;
+        h->seen_frames = h->seen_iters = h->seen_fails = 0; // the schedule statistics restart with the counters (everything queued
+        h->stat_pending = false;                            // has finished: dvbs2_cuda_sync above); what was learnt so far stays
+        if (h->stat_mirror) h->stat_mirror[0] = h->stat_mirror[1] = h->stat_mirror[2] = 0;
         h->launches = 0;
         if (h->mon.p) CU(h, cudaMemset(h->mon.p, 0, h->mon.bytes));
         TRY(prof_collect(h));

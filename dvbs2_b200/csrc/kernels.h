@@ -87,6 +87,7 @@ struct CompactLaunch
     void* var_dst;
     const uint4* cn_src;
     uint4* cn_dst;
+    int state_words; // 32-bit words of the compressed check state per (check, frame or int16 pair): ldpc_state_words(d_info)
     int n_groups, nf, cap, M;
     int nf_dst;                // frames per lane of the destination groups (<= nf)
 };
@@ -109,6 +110,7 @@ cudaError_t launch_ldpc_decode(const LdpcLaunch& a, int precision, cudaStream_t 
 cudaError_t launch_ldpc_decode_coop(const LdpcLaunch& a, cudaStream_t s);
 // smallest distance (in checks) between two checks sharing an information variable that the cooperative kernel tolerates
 int ldpc_coop_min_reuse();
+int ldpc_state_words(int d_info); // 32-bit words of compressed check state per (check, frame / int16 pair): 3 for degree <= 11, else 4
 cudaError_t launch_pack_llr(const void* in, void* var, int precision, int n_frames, int nf, cudaStream_t s);
 // int8 LLRs on the wire (compact input socket of the fixed-point decoder) into the int16 decoder's var layout
 cudaError_t launch_pack_llr8_as_i16(const int8_t* in, void* var, int n_frames, int nf, cudaStream_t s);

@@ -173,6 +173,45 @@ __device__ __forceinline__ int hi(uint32_t x) { return (int)(short)(x >> 16); }
 __device__ __forceinline__ uint32_t pair(int l, int h) { return ((uint32_t)l & 0xffffu) | ((uint32_t)h << 16); }
 } // namespace pk
 
+// ---------------------------------------------------------------------------------------------- check-state storage
+// Compressed check state of one (check, frame) — or (check, pair of frames) in the packed int16 kernel — is four 32-bit words
+// for the degree-27 checks of the rate-8/9 codes and THREE for the degree-11 checks of the rate-3/5 codes, whose sign and
+// "== min1" bits (or sign bits and argmin index) fit one word: 12 instead of 16 bytes, -25 % of the state traffic, -7 % of
+// all bytes these codes move per iteration.  Element e of a group = check * (frames or pairs per lane) + index in the lane.
+//   SW = 4: [element][lane] uint4 (one 16-byte access per lane, 512 contiguous bytes per warp)
+//   SW = 3: [element][word][lane] uint32 (three 128-byte rows per warp)
+// ldpc_state_words(d_info) in kernels.h tells the host side which one a code uses.
+template<int SW>
+struct StateIO
+{
+    static __device__ __forceinline__ size_t group_words(int M, int per_lane) { return (size_t)M * per_lane * SW * 32; }
+    // w[3] is 0 for SW = 3
+    static __device__ __forceinline__ uint4 load(const uint32_t* __restrict__ grp, size_t e, int lane)
+    {
+        if constexpr (SW == 4)
+            return __ldcg(reinterpret_cast<const uint4*>(grp) + e * 32 + lane);
+        else
+        {
+            const uint32_t* p = grp + e * (3 * 32) + lane;
+            return make_uint4(__ldcg(p), __ldcg(p + 32), __ldcg(p + 64), 0u);
+        }
+    }
+    static __device__ __forceinline__ void store(uint32_t* __restrict__ grp, size_t e, int lane, uint4 v)
+    {
+        if constexpr (SW == 4)
+            __stcg(reinterpret_cast<uint4*>(grp) + e * 32 + lane, v);
+        else
+        {
+            uint32_t* p = grp + e * (3 * 32) + lane;
+            __stcg(p, v.x), __stcg(p + 32, v.y), __stcg(p + 64, v.z);
+        }
+    }
+};
+// degree D = d_info + 2 edges: the sign bits and the "== min1" bits (16 each), or the sign bits and a 5-bit index per half in the
+// packed kernel (11 + 5), share a word when D <= 11
+template<int DI>
+constexpr int STATE_WORDS = (DI + 2 <= 11) ? 3 : 4;
+
 // ---------------------------------------------------------------------------------------------- the decoder
 template<typename R, int DI, int NF>
 struct CheckRegs
@@ -228,7 +267,9 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
         // byte offsets inside a group fit 32 bits: (warp-uniform base) + variable * VB + lane offset
         char* __restrict__ vbytes = (char*)a.var + (size_t)g * N_LDPC * VB;
         const unsigned loff = lane * NF * (unsigned)sizeof(R);
-        uint4* __restrict__ cn = a.cn + (size_t)g * M * NF * 32 + lane;
+        constexpr int SW = STATE_WORDS<DI>;
+        using SIO = StateIO<SW>;
+        uint32_t* __restrict__ cn = reinterpret_cast<uint32_t*>(a.cn) + (size_t)g * SIO::group_words(M, PK ? NF / 2 : NF);
         uint32_t* __restrict__ hd = a.hd + (size_t)g * NF * N_LDPC;       // running hard decisions, [v][NF] words
         uint32_t* __restrict__ out_hd = a.out_hd + (size_t)g * NF * N_LDPC; // final ones, [NF][v] (subgroup-major)
 
@@ -261,7 +302,6 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
             {
                 constexpr int NP = NF / 2;    // pairs per lane (2 in round 1; 1 in the narrower groups of the later rounds)
                 constexpr uint32_t ONE = 0x00010001u, MAXV = 0x7fff7fffu;
-                uint4* __restrict__ cnp = a.cn + (size_t)g * M * NP * 32 + lane; // [c][pair][lane]
                 const bool have_state = resumed || ite > 0;
                 bool pmine[NP];
 #pragma unroll
@@ -288,7 +328,10 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
                 auto load_state = [&](int c) {
 #pragma unroll
                     for (int p = 0; p < NP; p++)
-                        rst[p] = have_state ? __ldcg(cnp + (size_t)(c * NP + p) * 32) : make_uint4(0u, 0u, 0u, 0u);
+                    {
+                        rst[p] = have_state ? SIO::load(cn, (size_t)(c * NP + p), lane) : make_uint4(0u, 0u, 0u, 0u);
+                        if constexpr (SW == 3) rst[p].w = rst[p].z; // one word: signs in bits 0..10, argmin index in bits 11..15 of each half
+                    }
                 };
 #pragma unroll
                 for (int i = 0; i < D; i++)
@@ -423,8 +466,10 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
 #pragma unroll
                     for (int p = 0; p < NP; p++)
                         if (pmine[p])
-                            __stcg(cnp + (size_t)(c * NP + p) * 32,
-                                   make_uint4(c1[p], c2[p], ns0[p], ns1[p] | ((nidx[p] & 0x001f001fu) << 11)));
+                        {
+                            const uint32_t w3 = ns1[p] | ((nidx[p] & 0x001f001fu) << 11);
+                            SIO::store(cn, (size_t)(c * NP + p), lane, SW == 3 ? make_uint4(c1[p], c2[p], ns0[p] | w3, 0u) : make_uint4(c1[p], c2[p], ns0[p], w3));
+                        }
                 }
             }
             else
@@ -447,7 +492,10 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
                 r.v[DI] = __ldcg(reinterpret_cast<const Raw*>(vbytes + ((unsigned)(K + c) * VB + loff)));
 #pragma unroll
                 for (int j = 0; j < NF; j++)
-                    r.st[j] = have_state ? __ldcg(cn + (size_t)(c * NF + j) * 32) : make_uint4(0u, 0u, 0u, 0u);
+                {
+                    r.st[j] = have_state ? SIO::load(cn, (size_t)(c * NF + j), lane) : make_uint4(0u, 0u, 0u, 0u);
+                    if constexpr (SW == 3) r.st[j].w = r.st[j].z >> 16, r.st[j].z &= 0xffffu; // sign bits | "== min1" bits << 16
+                }
             };
 
             // One register set: pass 1 turns the loaded values into t = var - msg (Update_rule_MS.hxx:57-67), which frees
@@ -567,7 +615,7 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
                     {
                         unsigned hi;
                         const unsigned lo = A::pack(c1[j], c2[j], hi);
-                        __stcg(cn + (size_t)(c * NF + j) * 32, make_uint4(lo, hi, nsg[j], neq[j]));
+                        SIO::store(cn, (size_t)(c * NF + j), lane, SW == 3 ? make_uint4(lo, hi, nsg[j] | (neq[j] << 16), 0u) : make_uint4(lo, hi, nsg[j], neq[j]));
                     }
             }
             }
@@ -789,7 +837,9 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
 
         char* __restrict__ vbytes = (char*)a.var + (size_t)g * N_LDPC * VB;
         const unsigned loff = lane * (unsigned)sizeof(float);
-        uint4* __restrict__ cn = a.cn + (size_t)g * M * 32 + lane;
+        constexpr int SW = STATE_WORDS<DI>;
+        using SIO = StateIO<SW>;
+        uint32_t* __restrict__ cn = reinterpret_cast<uint32_t*>(a.cn) + (size_t)g * SIO::group_words(M, 1);
         uint32_t* __restrict__ hd = a.hd + (size_t)g * N_LDPC;
         uint32_t* __restrict__ out_hd = a.out_hd + (size_t)g * N_LDPC;
 
@@ -860,7 +910,8 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
                         v[i] = __ldcg(reinterpret_cast<const float*>(vbytes + (vi * VB + loff)));
                     }
                     v[DI] = __ldcg(reinterpret_cast<const float*>(vbytes + ((unsigned)(K + c) * VB + loff)));
-                    st = have_state ? __ldcg(cn + (size_t)c * 32) : make_uint4(0u, 0u, 0u, 0u);
+                    st = have_state ? SIO::load(cn, (size_t)c, lane) : make_uint4(0u, 0u, 0u, 0u);
+                    if constexpr (SW == 3) st.w = st.z >> 16, st.z &= 0xffffu;
                 };
                 uint32_t* sl = s_slot + w * SLOT + lane;
                 if (w < M) issue(w);
@@ -942,7 +993,10 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
                             if (lane == 0) __stcg(hd + vi, hw);
                         }
                     }
-                    if (mine) __stcg(cn + (size_t)c * 32, make_uint4(__float_as_uint(c1), __float_as_uint(c2), nsg, neq));
+                    if (mine)
+                        SIO::store(cn, (size_t)c, lane,
+                                   SW == 3 ? make_uint4(__float_as_uint(c1), __float_as_uint(c2), nsg | (neq << 16), 0u)
+                                           : make_uint4(__float_as_uint(c1), __float_as_uint(c2), nsg, neq));
                 }
             }
             my_iters += mine ? 1 : 0;
@@ -1076,9 +1130,10 @@ compact_expand_kernel(const CompactLaunch c)
 // warp = (destination group, part): gathers the state of its 32*ND survivors.  Survivors of one source group are
 // neighbours in destination order, so the scattered element loads of a warp fall into a handful of source chunks.
 constexpr int COMPACT_PARTS = 8;
-template<typename R, int NF, int ND> // NF: frames per lane of the source groups, ND: of the destination groups
+template<typename R, int NF, int ND, int SW = 4> // NF: frames per lane of the source groups, ND: of the destination groups; SW: state words
 __global__ void __launch_bounds__(128) compact_copy_kernel(const CompactLaunch c)
 {
+    using SIO = StateIO<SW>;
     const int lane = threadIdx.x & 31;
     const int d = blockIdx.x;
     const int part = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1094,7 +1149,8 @@ __global__ void __launch_bounds__(128) compact_copy_kernel(const CompactLaunch c
         const int s = valid[j] ? c.src_of_dst[ds] : 0;
         const int gs = s / (32 * NF), js = (s / 32) % NF, ls = s % 32;
         vbase[j] = ((size_t)gs * N_LDPC * 32 + ls) * NF + js;
-        cbase[j] = ((size_t)gs * c.M * NF + js) * 32 + ls;
+        cbase[j] = (size_t)gs; // source group; element and lane follow from js, ls below
+        (void)ls;
     }
     const R* vs = (const R*)c.var_src;
     R* vd = (R*)c.var_dst + ((size_t)d * N_LDPC * 32 + lane) * ND;
@@ -1110,22 +1166,25 @@ __global__ void __launch_bounds__(128) compact_copy_kernel(const CompactLaunch c
         for (int j = 0; j < ND; j++)
             vd[(size_t)v * 32 * ND + j] = x[j];
     }
-    uint4* cd = c.cn_dst + (size_t)d * c.M * (sizeof(R) == 2 ? ND / 2 : ND) * 32 + lane;
+    constexpr int PLS = sizeof(R) == 2 ? NF / 2 : NF, PLD = sizeof(R) == 2 ? ND / 2 : ND; // state elements per lane: pairs for int16
+    const uint32_t* cs = reinterpret_cast<const uint32_t*>(c.cn_src);
+    uint32_t* cd = reinterpret_cast<uint32_t*>(c.cn_dst) + (size_t)d * SIO::group_words(c.M, PLD);
+    int src_js[ND], src_ls[ND];
+#pragma unroll
+    for (int j = 0; j < ND; j++)
+    {
+        const int ds = (d * ND + j) * 32 + lane;
+        const int sl = valid[j] ? c.src_of_dst[ds] : 0;
+        src_js[j] = (sl / 32) % NF, src_ls[j] = sl % 32;
+    }
     const int c0 = (int)((long)c.M * part / COMPACT_PARTS), c1 = (int)((long)c.M * (part + 1) / COMPACT_PARTS);
     if constexpr (sizeof(R) == 2)
     { // packed pairs (ldpc_decode_kernel<int16_t, ., 4, true>): state [check][pair][lane], one half of every word per frame
         static_assert((NF == 4 || NF == 2) && (ND == 4 || ND == 2), "int16_t groups hold two or four frames per lane");
-        size_t pbase[ND];
         int sh[ND];
 #pragma unroll
         for (int j = 0; j < ND; j++)
-        {
-            const int ds = (d * ND + j) * 32 + lane;
-            const int s = valid[j] ? c.src_of_dst[ds] : 0;
-            const int gs = s / (32 * NF), js = (s / 32) % NF, ls = s % 32;
-            pbase[j] = ((size_t)gs * c.M * (NF / 2) + (js >> 1)) * 32 + ls;
-            sh[j] = (js & 1) * 16;
-        }
+            sh[j] = (src_js[j] & 1) * 16;
 #pragma unroll 2
         for (int k = c0; k < c1; k++)
 #pragma unroll
@@ -1137,13 +1196,13 @@ __global__ void __launch_bounds__(128) compact_copy_kernel(const CompactLaunch c
                 {
                     const int j = 2 * p + hf;
                     if (!valid[j]) continue;
-                    const uint4 x = __ldcg(c.cn_src + pbase[j] + (size_t)k * (NF / 2) * 32);
+                    const uint4 x = SIO::load(cs + cbase[j] * SIO::group_words(c.M, PLS), (size_t)k * PLS + (src_js[j] >> 1), src_ls[j]);
                     w[0] |= ((x.x >> sh[j]) & 0xffffu) << (16 * hf);
                     w[1] |= ((x.y >> sh[j]) & 0xffffu) << (16 * hf);
                     w[2] |= ((x.z >> sh[j]) & 0xffffu) << (16 * hf);
                     w[3] |= ((x.w >> sh[j]) & 0xffffu) << (16 * hf);
                 }
-                cd[(size_t)(k * (ND / 2) + p) * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+                SIO::store(cd, (size_t)k * PLD + p, lane, make_uint4(w[0], w[1], w[2], w[3]));
             }
     }
     else
@@ -1152,7 +1211,9 @@ __global__ void __launch_bounds__(128) compact_copy_kernel(const CompactLaunch c
         for (int k = c0; k < c1; k++)
 #pragma unroll
             for (int j = 0; j < ND; j++)
-                cd[(size_t)(k * ND + j) * 32] = valid[j] ? __ldcg(c.cn_src + cbase[j] + (size_t)k * NF * 32) : make_uint4(0u, 0u, 0u, 0u);
+                SIO::store(cd, (size_t)k * PLD + j, lane,
+                           valid[j] ? SIO::load(cs + cbase[j] * SIO::group_words(c.M, PLS), (size_t)k * PLS + src_js[j], src_ls[j])
+                                    : make_uint4(0u, 0u, 0u, 0u));
     }
 }
 
@@ -1369,8 +1430,21 @@ launch_compact_t(const CompactLaunch& c, cudaStream_t s)
     compact_scan_kernel<<<1, 1024, 0, s>>>(c); count_launch();
     compact_expand_kernel<<<(c.n_groups * c.nf + 127) / 128, 128, 0, s>>>(c); count_launch();
     const dim3 grid(c.cap / (32 * ND), (COMPACT_PARTS + 3) / 4);
-    if (grid.x > 0) { compact_copy_kernel<R, NF, ND><<<grid, 128, 0, s>>>(c); count_launch(); }
+    if (grid.x > 0)
+    {
+        if (c.state_words == 3)
+            compact_copy_kernel<R, NF, ND, 3><<<grid, 128, 0, s>>>(c);
+        else
+            compact_copy_kernel<R, NF, ND, 4><<<grid, 128, 0, s>>>(c);
+        count_launch();
+    }
     return cudaGetLastError();
+}
+
+int
+ldpc_state_words(int d_info)
+{
+    return d_info == 9 ? STATE_WORDS<9> : STATE_WORDS<25>;
 }
 
 int
