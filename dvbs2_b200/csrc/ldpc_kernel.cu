@@ -185,24 +185,25 @@ template<int SW>
 struct StateIO
 {
     static __device__ __forceinline__ size_t group_words(int M, int per_lane) { return (size_t)M * per_lane * SW * 32; }
-    // w[3] is 0 for SW = 3
-    static __device__ __forceinline__ uint4 load(const uint32_t* __restrict__ grp, size_t e, int lane)
+    // `at` = first word of the group + the lane's offset (lane_offset()); w[3] of the result is 0 for SW = 3
+    static __device__ __forceinline__ int lane_offset(int lane) { return SW == 4 ? 4 * lane : lane; }
+    static __device__ __forceinline__ uint4 load(const uint32_t* __restrict__ at, size_t e)
     {
         if constexpr (SW == 4)
-            return __ldcg(reinterpret_cast<const uint4*>(grp) + e * 32 + lane);
+            return __ldcg(reinterpret_cast<const uint4*>(at) + e * 32);
         else
         {
-            const uint32_t* p = grp + e * (3 * 32) + lane;
+            const uint32_t* p = at + e * (3 * 32);
             return make_uint4(__ldcg(p), __ldcg(p + 32), __ldcg(p + 64), 0u);
         }
     }
-    static __device__ __forceinline__ void store(uint32_t* __restrict__ grp, size_t e, int lane, uint4 v)
+    static __device__ __forceinline__ void store(uint32_t* __restrict__ at, size_t e, uint4 v)
     {
         if constexpr (SW == 4)
-            __stcg(reinterpret_cast<uint4*>(grp) + e * 32 + lane, v);
+            __stcg(reinterpret_cast<uint4*>(at) + e * 32, v);
         else
         {
-            uint32_t* p = grp + e * (3 * 32) + lane;
+            uint32_t* p = at + e * (3 * 32);
             __stcg(p, v.x), __stcg(p + 32, v.y), __stcg(p + 64, v.z);
         }
     }
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
         const unsigned loff = lane * NF * (unsigned)sizeof(R);
         constexpr int SW = STATE_WORDS<DI>;
         using SIO = StateIO<SW>;
-        uint32_t* __restrict__ cn = reinterpret_cast<uint32_t*>(a.cn) + (size_t)g * SIO::group_words(M, PK ? NF / 2 : NF);
+        uint32_t* __restrict__ cn = reinterpret_cast<uint32_t*>(a.cn) + (size_t)g * SIO::group_words(M, PK ? NF / 2 : NF) + SIO::lane_offset(lane);
         uint32_t* __restrict__ hd = a.hd + (size_t)g * NF * N_LDPC;       // running hard decisions, [v][NF] words
         uint32_t* __restrict__ out_hd = a.out_hd + (size_t)g * NF * N_LDPC; // final ones, [NF][v] (subgroup-major)
 
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
 #pragma unroll
                     for (int p = 0; p < NP; p++)
                     {
-                        rst[p] = have_state ? SIO::load(cn, (size_t)(c * NP + p), lane) : make_uint4(0u, 0u, 0u, 0u);
+                        rst[p] = have_state ? SIO::load(cn, (size_t)(c * NP + p)) : make_uint4(0u, 0u, 0u, 0u);
                         if constexpr (SW == 3) rst[p].w = rst[p].z; // one word: signs in bits 0..10, argmin index in bits 11..15 of each half
                     }
                 };
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
                         if (pmine[p])
                         {
                             const uint32_t w3 = ns1[p] | ((nidx[p] & 0x001f001fu) << 11);
-                            SIO::store(cn, (size_t)(c * NP + p), lane, SW == 3 ? make_uint4(c1[p], c2[p], ns0[p] | w3, 0u) : make_uint4(c1[p], c2[p], ns0[p], w3));
+                            SIO::store(cn, (size_t)(c * NP + p), SW == 3 ? make_uint4(c1[p], c2[p], ns0[p] | w3, 0u) : make_uint4(c1[p], c2[p], ns0[p], w3));
                         }
                 }
             }
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
 #pragma unroll
                 for (int j = 0; j < NF; j++)
                 {
-                    r.st[j] = have_state ? SIO::load(cn, (size_t)(c * NF + j), lane) : make_uint4(0u, 0u, 0u, 0u);
+                    r.st[j] = have_state ? SIO::load(cn, (size_t)(c * NF + j)) : make_uint4(0u, 0u, 0u, 0u);
                     if constexpr (SW == 3) r.st[j].w = r.st[j].z >> 16, r.st[j].z &= 0xffffu; // sign bits | "== min1" bits << 16
                 }
             };
@@ -615,7 +616,7 @@ __global__ void __launch_bounds__(LDPC_WARPS * 32, 1) ldpc_decode_kernel(const L
                     {
                         unsigned hi;
                         const unsigned lo = A::pack(c1[j], c2[j], hi);
-                        SIO::store(cn, (size_t)(c * NF + j), lane, SW == 3 ? make_uint4(lo, hi, nsg[j] | (neq[j] << 16), 0u) : make_uint4(lo, hi, nsg[j], neq[j]));
+                        SIO::store(cn, (size_t)(c * NF + j), SW == 3 ? make_uint4(lo, hi, nsg[j] | (neq[j] << 16), 0u) : make_uint4(lo, hi, nsg[j], neq[j]));
                     }
             }
             }
@@ -839,7 +840,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
         const unsigned loff = lane * (unsigned)sizeof(float);
         constexpr int SW = STATE_WORDS<DI>;
         using SIO = StateIO<SW>;
-        uint32_t* __restrict__ cn = reinterpret_cast<uint32_t*>(a.cn) + (size_t)g * SIO::group_words(M, 1);
+        uint32_t* __restrict__ cn = reinterpret_cast<uint32_t*>(a.cn) + (size_t)g * SIO::group_words(M, 1) + SIO::lane_offset(lane);
         uint32_t* __restrict__ hd = a.hd + (size_t)g * N_LDPC;
         uint32_t* __restrict__ out_hd = a.out_hd + (size_t)g * N_LDPC;
 
@@ -910,7 +911,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
                         v[i] = __ldcg(reinterpret_cast<const float*>(vbytes + (vi * VB + loff)));
                     }
                     v[DI] = __ldcg(reinterpret_cast<const float*>(vbytes + ((unsigned)(K + c) * VB + loff)));
-                    st = have_state ? SIO::load(cn, (size_t)c, lane) : make_uint4(0u, 0u, 0u, 0u);
+                    st = have_state ? SIO::load(cn, (size_t)c) : make_uint4(0u, 0u, 0u, 0u);
                     if constexpr (SW == 3) st.w = st.z >> 16, st.z &= 0xffffu;
                 };
                 uint32_t* sl = s_slot + w * SLOT + lane;
@@ -994,7 +995,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
                         }
                     }
                     if (mine)
-                        SIO::store(cn, (size_t)c, lane,
+                        SIO::store(cn, (size_t)c,
                                    SW == 3 ? make_uint4(__float_as_uint(c1), __float_as_uint(c2), nsg | (neq << 16), 0u)
                                            : make_uint4(__float_as_uint(c1), __float_as_uint(c2), nsg, neq));
                 }
@@ -1168,7 +1169,7 @@ __global__ void __launch_bounds__(128) compact_copy_kernel(const CompactLaunch c
     }
     constexpr int PLS = sizeof(R) == 2 ? NF / 2 : NF, PLD = sizeof(R) == 2 ? ND / 2 : ND; // state elements per lane: pairs for int16
     const uint32_t* cs = reinterpret_cast<const uint32_t*>(c.cn_src);
-    uint32_t* cd = reinterpret_cast<uint32_t*>(c.cn_dst) + (size_t)d * SIO::group_words(c.M, PLD);
+    uint32_t* cd = reinterpret_cast<uint32_t*>(c.cn_dst) + (size_t)d * SIO::group_words(c.M, PLD) + SIO::lane_offset(lane);
     int src_js[ND], src_ls[ND];
 #pragma unroll
     for (int j = 0; j < ND; j++)
@@ -1196,13 +1197,13 @@ __global__ void __launch_bounds__(128) compact_copy_kernel(const CompactLaunch c
                 {
                     const int j = 2 * p + hf;
                     if (!valid[j]) continue;
-                    const uint4 x = SIO::load(cs + cbase[j] * SIO::group_words(c.M, PLS), (size_t)k * PLS + (src_js[j] >> 1), src_ls[j]);
+                    const uint4 x = SIO::load(cs + cbase[j] * SIO::group_words(c.M, PLS) + SIO::lane_offset(src_ls[j]), (size_t)k * PLS + (src_js[j] >> 1));
                     w[0] |= ((x.x >> sh[j]) & 0xffffu) << (16 * hf);
                     w[1] |= ((x.y >> sh[j]) & 0xffffu) << (16 * hf);
                     w[2] |= ((x.z >> sh[j]) & 0xffffu) << (16 * hf);
                     w[3] |= ((x.w >> sh[j]) & 0xffffu) << (16 * hf);
                 }
-                SIO::store(cd, (size_t)k * PLD + p, lane, make_uint4(w[0], w[1], w[2], w[3]));
+                SIO::store(cd, (size_t)k * PLD + p, make_uint4(w[0], w[1], w[2], w[3]));
             }
     }
     else
@@ -1211,8 +1212,8 @@ __global__ void __launch_bounds__(128) compact_copy_kernel(const CompactLaunch c
         for (int k = c0; k < c1; k++)
 #pragma unroll
             for (int j = 0; j < ND; j++)
-                SIO::store(cd, (size_t)k * PLD + j, lane,
-                           valid[j] ? SIO::load(cs + cbase[j] * SIO::group_words(c.M, PLS), (size_t)k * PLS + src_js[j], src_ls[j])
+                SIO::store(cd, (size_t)k * PLD + j,
+                           valid[j] ? SIO::load(cs + cbase[j] * SIO::group_words(c.M, PLS) + SIO::lane_offset(src_ls[j]), (size_t)k * PLS + src_js[j])
                                     : make_uint4(0u, 0u, 0u, 0u));
     }
 }

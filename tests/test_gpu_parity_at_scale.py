@@ -160,8 +160,8 @@ def test_three_round_path_at_bench_scale(ref, oracle, modcod, prec):
     dec.decode_siho_dev(Y, cwd2, V2, nit2)
     st2 = h.stats()
     h.close()
-    mean_it = st["ldpc_iterations"] / st["frames"]
-    if 4.5 <= mean_it <= 9.0:
+    mean_it, fail = st["ldpc_iterations"] / st["frames"], st["ldpc_failures"] / st["frames"]
+    if 4.5 <= mean_it <= 9.0 and fail <= (0.2 if prec == "f32" else 0.08):  # pick_schedule() of capi.cu
         assert st2["kernel_launches"] - st["kernel_launches"] >= st["kernel_launches"] + 4, (st["kernel_launches"], st2["kernel_launches"])
     assert torch.equal(cwd2, cwd) and torch.equal(nit2, nit)
     for a in range(0, F, 32768):
