@@ -555,6 +555,8 @@ def main():
             e2e["sockets"] = socks
             if "f32_int32" in socks:
                 e2e["matches_device_path"] = socks["f32_int32"].get("matches_device_path")
+        else:  # every format failed: keep the reasons
+            e2e = {"value": None, "sockets": socks}
 
     tp = lap("e2e", tp)
     # ---- CPU baseline beside it (rank 0, N=1 only): the compiled reference on this box's host cores, bounded sample

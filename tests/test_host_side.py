@@ -193,11 +193,11 @@ def test_counter_reduction_world_size_2_gloo():
 
 
 def test_committed_bench_line_follows_the_driver_contract():
-    """The bench line recorded from the final code of the round (profiles/r1_bench_v10.json) carries every key the driver and
+    """The bench line recorded from the final code of the round (profiles/r2_final_bench.json) carries every key the driver and
     the judge read, with consistent values."""
     import json
 
-    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_v10.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_final_bench.json")))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in d, k
@@ -210,9 +210,13 @@ def test_committed_bench_line_follows_the_driver_contract():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["matches_device_path"] is True
     assert e["value"] < d["value"]  # host buffers over PCIe cannot beat the device-resident rate
+    assert set(e["sockets"]) >= {"f32_int32", "sc16_packed"} and e["headline_sockets"] == "sc16_packed"
+    for name, line in d["configs"].items():  # BASELINE configs 2-4 are lines of the same object
+        assert line["value"] > 0 and line["roofline"]["frac"] > 0, name
+    assert d["int16"]["value"] > d["value"] and sum(d["iter_hist"]) == d["fer"]["frames"]
     K_bch = 14232
     frames = d["config"]["frames_per_step_per_gpu"] * d["steps"] * d["n_gpus"]
     assert abs(d["value"] - K_bch * frames / (d["ms_per_step"] * d["steps"] * 1e-3) / 1e6) / d["value"] < 1e-3
-    ref = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_v10_reference_arm.json")))
+    ref = json.load(open(os.path.join(ROOT, "profiles", "r2_final_bench_reference_arm.json")))
     assert ref["impl"] == "reference" and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] == "reference"
