@@ -409,6 +409,7 @@ def main():
         h = None
         del V, chain, tx
         batches = batches[:1]
+        sig = rx = None  # the loop variables of the batch generation still held the last batch
         torch.cuda.empty_cache()
         default_fmts = "llr8_packed" if args.prec == "i16" else "f32_int32,f32_packed,sc16_packed,sc8_packed"
         fmts = [f for f in (args.e2e_sockets or default_fmts).split(",") if f]
@@ -440,9 +441,16 @@ def main():
             prec = "i16" if in_kind == "llr8" else args.prec
             chunks = args.e2e_chunks if args.e2e_chunks >= 0 else (1 if NC > 1 else 0)
             clones, same = [], None
+            gpu_free0 = torch.cuda.mem_get_info(dev)[0]
             for c in range(NC):
-                hc = Handle(modcod=modcod, n_ite=args.ite, norm=1.0, precision=prec, early_stop=True, n_frames=Fe, device=local,
-                            host_pipeline_chunks=chunks, **tune)
+                try:
+                    hc = Handle(modcod=modcod, n_ite=args.ite, norm=1.0, precision=prec, early_stop=True, n_frames=Fe, device=local,
+                                host_pipeline_chunks=chunks, **tune)
+                except Exception as e:  # noqa: BLE001
+                    for old in clones:
+                        old[0].close()
+                    raise RuntimeError("clone %d of %d x %d frames: %r (GPU memory free before the clones %.1f GB, now %.1f GB)"
+                                       % (c, NC, Fe, e, gpu_free0 / 1e9, torch.cuda.mem_get_info(dev)[0] / 1e9))
                 o = (c * Fe) % max(1, F - Fe + 1)  # clones take disjoint slices of batch 0 while they fit (always, by default)
                 src_sig, src_rx = batches[0][0][o:o + Fe], batches[0][1][o:o + Fe]
                 hs = pin(Fe, dtype=torch.float32)
@@ -503,6 +511,7 @@ def main():
             run_clones(max(1, min(args.warmup, 2)))
             for hc, _, _, _ in clones:
                 hc.reset_stats()
+            clones[0][0].set_profiling(True)  # device time per stage of clone 0's calls while the other clones share the GPU
             barrier()
             torch.cuda.synchronize()
             w0 = time.perf_counter()
@@ -512,6 +521,8 @@ def main():
             w = reduce_([w], dist.ReduceOp.MAX if world > 1 else None)[0]
             barrier()
             n_launch = sum(hc.stats()["kernel_launches"] for hc, _, _, _ in clones)
+            tm0 = clones[0][0].timers()
+            stage0 = {k[:-3]: round(tm0[k] / max(1, tm0[k[:-3] + "_calls"]), 3) for k in tm0 if k.endswith("_ms") and tm0[k[:-3] + "_calls"]}
             fails = sum(int((a["c2"] == 0).sum()) for _, _, a, _ in clones)
             if fmt == "f32_int32":  # the host result of clone 0 equals the device-resident result of the same frames
                 same = bool(np.array_equal(clones[0][2]["V"][:len(V_head)], V_head[:Fe]))
@@ -526,7 +537,7 @@ def main():
                  "host_gbs_per_gpu": round(NC * (in_b + out_b) * args.steps / w / 1e9, 2),
                  "host_gbs_total": round(world * NC * (in_b + out_b) * args.steps / w / 1e9, 2),
                  "frames_per_step_per_gpu": Fe * NC, "clones": NC, "ms_per_step": round(w / args.steps * 1e3, 3),
-                 "gpu_launches": int(n_launch), "bch_fer": round(fails / (Fe * NC), 5)}
+                 "gpu_launches": int(n_launch), "bch_fer": round(fails / (Fe * NC), 5), "clone0_stage_ms_per_call": stage0}
             if same is not None:
                 r["matches_device_path"] = same
             return r
@@ -542,7 +553,7 @@ def main():
                 socks[fmt] = e2e_run(fmt)
                 socks[fmt]["api"] = API.get(fmt, fmt)
             except Exception as e:  # noqa: BLE001
-                socks[fmt] = {"value": None, "error": repr(e)[:300]}
+                socks[fmt] = {"value": None, "error": repr(e)[:400], "gpu_free_gb_after_failure": round(torch.cuda.mem_get_info(dev)[0] / 1e9, 1)}
             torch.cuda.empty_cache()
         head = next((f for f in ("sc16_packed", "llr8_packed", "f32_packed", "f32_int32") if socks.get(f, {}).get("value")), None)
         if head:
