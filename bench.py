@@ -65,6 +65,7 @@ def parse():
     p.add_argument("--rounds", type=int, default=0, help="decoding rounds (frame compaction between rounds); 0 = library default")
     p.add_argument("--exit-eighths", type=int, default=0, help="hand-over threshold in eighths of a group; 0 = library default")
     p.add_argument("--nf-later", type=int, default=0, help="f32: frames per lane in rounds >= 2; 0 = library default")
+    p.add_argument("--nf-first", type=int, default=0, help="f32: frames per lane in round 1 (1 = 32-frame groups, 2 = 64-frame groups); 0 = library default (by batch size)")
     p.add_argument("--coop-max", type=int, default=0, help="f32: largest call that uses the cooperative small-batch LDPC kernel (0 = library default 16384, -1 = never)")
     p.add_argument("--onchip", type=int, default=0, help="f32: 1 = the on-chip LDPC kernel (design B), -1 = never, 0 = library default")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -297,7 +298,8 @@ def main():
             F = int(t.item())
 
     tune = dict(compaction=not args.no_compaction, compaction_rounds=args.rounds, compaction_exit_eighths=args.exit_eighths,
-                compaction_nf_later=args.nf_later, ldpc_coop_max_frames=args.coop_max, ldpc_onchip=args.onchip)
+                compaction_nf_later=args.nf_later, ldpc_coop_max_frames=args.coop_max, ldpc_onchip=args.onchip,
+                ldpc_frames_per_lane=args.nf_first)
     h = Handle(modcod=modcod, n_ite=args.ite, norm=1.0, precision=args.prec, early_stop=True, n_frames=F, device=local, **tune)
     chain = Decoder_chain_DVBS2_cuda(h, F)
     # synthetic frames made where they are decoded: random payload -> BB scramble -> BCH -> LDPC -> interleave -> map -> AWGN
