@@ -53,7 +53,7 @@ def parse():
     p.add_argument("--ite", type=int, default=10)
     p.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the largest of 3, 2, 1 waves of the LDPC kernel = SMs x 12 warps x 64 frames each that fits in 80 %% of the free HBM)")
     p.add_argument("--e2e-frames", type=int, default=0, help="frames per e2e call of one module clone (default: one wave of the LDPC kernel)")
-    p.add_argument("--e2e-clones", type=int, default=4, help="module clones (handles + host threads) of the e2e run; 4 keeps the GPU busiest (3: 0.80-0.83 of the device-resident rate, 4-5: 0.85, 6 does not fit in HBM)")
+    p.add_argument("--e2e-clones", type=int, default=0, help="module clones (handles + host threads) of the e2e run; 0 = automatic: 4 x one wave per call for the float sockets (3: 0.80-0.83 of the device-resident rate, 4-5: 0.85, 6 does not fit in HBM), 2 x the whole batch per call for the compact sockets")
     p.add_argument("--e2e-chunks", type=int, default=-1, help="host_pipeline_chunks of the e2e clones (-1: 1 when there are several clones, else automatic)")
     p.add_argument("--e2e-sockets", default="", help="comma list of socket formats to time (default: f32_int32,f32_packed,sc16_packed,sc8_packed; llr8_packed with --prec i16)")
     p.add_argument("--no-configs", action="store_true", help="skip the extra lines for BASELINE configs 2-4")
@@ -401,7 +401,8 @@ def main():
     # format; the clones of a format are created, timed and destroyed before the next format allocates its buffers.
     e2e = None
     if not args.no_e2e:
-        NC = max(1, args.e2e_clones)
+        args.e2e_clones_given = args.e2e_clones > 0
+        NC0 = args.e2e_clones if args.e2e_clones > 0 else 4
         # device-resident result of the first frames of batch 0 (what clone 0 decodes), then the big decoder state goes: the e2e
         # clones bring their own handles
         step(0)
@@ -410,7 +411,10 @@ def main():
         h.close()
         h = None
         del V, chain, tx
-        batches = batches[:1]
+        # batch 0 moves to host memory (the e2e inputs live there anyway) and every device batch goes: the clones of the compact
+        # formats then have room for three-wave calls
+        host0 = (batches[0][0].cpu(), batches[0][1].cpu())
+        batches = None
         sig = rx = None  # the loop variables of the batch generation still held the last batch
         torch.cuda.empty_cache()
         default_fmts = "llr8_packed" if args.prec == "i16" else "f32_int32,f32_packed,sc16_packed,sc8_packed"
@@ -418,13 +422,27 @@ def main():
         SC16, SC8 = 1.0 / 8192, 1.0 / 32  # LSB of the integer I/Q formats: +-4.0 full scale (unit-energy constellations)
         pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()  # noqa: E731
 
-        def e2e_run(fmt):
+        def e2e_run(fmt, allow_big=True):
             in_kind, out_kind = fmt.split("_")
             # one call of a clone = one wave of the LDPC kernel (every launch fills the machine; the copies of one clone overlap
             # the kernels of the others, so calls are not chunked).  The reference's int32-per-bit sockets need 14 GB of pinned
             # memory per wave and clone: half a wave there when eight ranks share one host.
-            Fe = args.e2e_frames if args.e2e_frames > 0 else (wave // 2 if (fmt == "f32_int32" and world > 1) else wave)
-            Fe = max(256, min(F if args.e2e_frames > 0 else F // NC, Fe) // 256 * 256)
+            # Call shape.  The reference's float sockets: NC clones x one wave per call (their staging buffers leave no room for
+            # more).  Compact input sockets: TWO clones x the whole device-resident batch per call — every LDPC launch then has the
+            # three waves that make the device-resident figure (single-wave launches lose 15 % to their tails: 16.7 against
+            # 19.7 Gbit/s), and the copies of one clone still lie under the kernels of the other.  --e2e-frames / --e2e-clones
+            # given explicitly pin the shape.
+            NC = NC0
+            hpf = {"f32": 195e3, "i16": 118e3, "i8": 80e3}["i16" if in_kind == "llr8" else args.prec]  # handle bytes per frame (measured)
+            big = allow_big and in_kind != "f32" and args.e2e_frames == 0 and not args.e2e_clones_given
+            if big:
+                need = 2 * F * (hpf + ({"sc16": 4, "sc8": 2}.get(in_kind, 0) * n_sym or N_LDPC) + K_bch // 8 + 64)
+                big = need < 0.97 * torch.cuda.mem_get_info(dev)[0]
+            if big:
+                NC, Fe = 2, F
+            else:
+                Fe = args.e2e_frames if args.e2e_frames > 0 else (wave // 2 if (fmt == "f32_int32" and world > 1) else wave)
+                Fe = max(256, min(F if args.e2e_frames > 0 else F // NC, Fe) // 256 * 256)
             # page-locked host memory of all clones must fit beside everything else in this box's RAM (shared by all ranks)
             in_kind0, out_kind0 = fmt.split("_")
             per_frame_host = ({"f32": 8, "sc16": 4, "sc8": 2}.get(in_kind0, 0) * n_sym or N_LDPC) + (4 * K_bch if out_kind0 == "int32" else K_bch // 8) + 16
@@ -436,13 +454,50 @@ def main():
                     Fe = max(8192, int(budget / (NC * per_frame_host)) // 256 * 256)
             except ImportError:
                 pass
-            if world > 1:  # the value is computed from one Fe: every rank uses the smallest
-                t = torch.tensor([Fe], dtype=torch.int64, device=dev)
+            if world > 1:  # the value is computed from one shape: every rank uses the smallest
+                t = torch.tensor([Fe, NC], dtype=torch.int64, device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MIN)
-                Fe = int(t.item())
+                Fe, NC = int(t[0].item()), int(t[1].item())
             prec = "i16" if in_kind == "llr8" else args.prec
             chunks = args.e2e_chunks if args.e2e_chunks >= 0 else (1 if NC > 1 else 0)
             clones, same = [], None
+            # ---- phase 1: the host (socket) buffers of every clone, made with device temporaries that are gone before the handles come
+            host_bufs = []
+            for c in range(NC):
+                o = (c * Fe) % max(1, F - Fe + 1)  # clones take disjoint slices of batch 0 while they fit
+                hs = pin(Fe, dtype=torch.float32)
+                hs.copy_(host0[0][o:o + Fe])
+                hc1, hc2, hn = pin(Fe, dtype=torch.int8), pin(Fe, dtype=torch.int8), pin(Fe, dtype=torch.int32)
+                if in_kind == "f32":
+                    hx = pin(Fe, 2 * n_sym, dtype=torch.float32)
+                    hx.copy_(host0[1][o:o + Fe])
+                elif in_kind in ("sc16", "sc8"):  # the radio's ADC words: quantised once, outside the timed region
+                    sc, lim, dt = (SC16, 32767, torch.int16) if in_kind == "sc16" else (SC8, 127, torch.int8)
+                    hx = pin(Fe, 2 * n_sym, dtype=dt)
+                    for a0 in range(0, Fe, wave):  # a wave at a time through the device
+                        q = host0[1][o + a0:o + min(Fe, a0 + wave)].to(dev) * (1.0 / sc)
+                        hx[a0:a0 + q.shape[0]].copy_((torch.sign(q) * torch.floor(torch.abs(q) + 0.5)).clamp_(-lim, lim).to(dt))
+                        del q
+                else:  # llr8: Quantizer_pow2(6, 2) outputs of the demapper's LLRs, one int8 per LLR
+                    hx = pin(Fe, N_LDPC, dtype=torch.int8)
+                    Fs = min(Fe, 113664)
+                    hf = Handle(modcod=modcod, n_frames=Fs, device=local)
+                    llr = torch.empty((Fs, N_LDPC), dtype=torch.float32, device=dev)
+                    for a0 in range(0, Fe, Fs):
+                        n = min(Fs, Fe - a0)
+                        ssig, srx = host0[0][o + a0:o + a0 + n].to(dev), host0[1][o + a0:o + a0 + n].to(dev)
+                        torch.cuda.synchronize()
+                        Modem_DVBS2_cuda(hf, n).demodulate_dev(ssig, srx, llr[:n], deinterleave=True)
+                        hf.sync()
+                        q = llr[:n] * 4.0
+                        hx[a0:a0 + n].copy_((torch.sign(q) * torch.floor(torch.abs(q) + 0.5)).clamp_(-31, 31).to(torch.int8))
+                        del q, ssig, srx
+                    hf.close()
+                    del llr
+                hV = pin(Fe, K_bch, dtype=torch.int32) if out_kind == "int32" else pin(Fe, K_bch // 8, dtype=torch.uint8)
+                host_bufs.append((hs, hx, hV, hc1, hc2, hn))
+            torch.cuda.empty_cache()
+            # ---- phase 2: one handle per clone
             gpu_free0 = torch.cuda.mem_get_info(dev)[0]
             for c in range(NC):
                 try:
@@ -451,33 +506,13 @@ def main():
                 except Exception as e:  # noqa: BLE001
                     for old in clones:
                         old[0].close()
+                    if big:  # the estimate was too tight for this box: the one-wave shape instead
+                        del clones, host_bufs
+                        torch.cuda.empty_cache()
+                        return e2e_run(fmt, allow_big=False)
                     raise RuntimeError("clone %d of %d x %d frames: %r (GPU memory free before the clones %.1f GB, now %.1f GB)"
                                        % (c, NC, Fe, e, gpu_free0 / 1e9, torch.cuda.mem_get_info(dev)[0] / 1e9))
-                o = (c * Fe) % max(1, F - Fe + 1)  # clones take disjoint slices of batch 0 while they fit (always, by default)
-                src_sig, src_rx = batches[0][0][o:o + Fe], batches[0][1][o:o + Fe]
-                hs = pin(Fe, dtype=torch.float32)
-                hs.copy_(src_sig)
-                hc1, hc2, hn = pin(Fe, dtype=torch.int8), pin(Fe, dtype=torch.int8), pin(Fe, dtype=torch.int32)
-                if in_kind == "f32":
-                    hx = pin(Fe, 2 * n_sym, dtype=torch.float32)
-                    hx.copy_(src_rx)
-                elif in_kind in ("sc16", "sc8"):  # the radio's ADC words: quantised once, outside the timed region
-                    sc, lim, dt = (SC16, 32767, torch.int16) if in_kind == "sc16" else (SC8, 127, torch.int8)
-                    hx = pin(Fe, 2 * n_sym, dtype=dt)
-                    q = src_rx * (1.0 / sc)
-                    hx.copy_((torch.sign(q) * torch.floor(torch.abs(q) + 0.5)).clamp_(-lim, lim).to(dt))
-                else:  # llr8: Quantizer_pow2(6, 2) outputs of the demapper's LLRs, one int8 per LLR
-                    hx = pin(Fe, N_LDPC, dtype=torch.int8)
-                    llr = torch.empty((Fe, N_LDPC), dtype=torch.float32, device=dev)
-                    hf = Handle(modcod=modcod, n_frames=Fe, device=local)
-                    torch.cuda.synchronize()
-                    Modem_DVBS2_cuda(hf, Fe).demodulate_dev(src_sig.contiguous(), src_rx.contiguous(), llr, deinterleave=True)
-                    hf.sync()
-                    hf.close()
-                    q = llr * 4.0
-                    hx.copy_((torch.sign(q) * torch.floor(torch.abs(q) + 0.5)).clamp_(-31, 31).to(torch.int8))
-                    del llr
-                hV = pin(Fe, K_bch, dtype=torch.int32) if out_kind == "int32" else pin(Fe, K_bch // 8, dtype=torch.uint8)
+                hs, hx, hV, hc1, hc2, hn = host_bufs[c]
                 a = dict(sig=hs.numpy(), x=hx.numpy(), c1=hc1.numpy(), c2=hc2.numpy(), n=hn.numpy(), V=hV.numpy())
                 if in_kind == "f32":
                     m = Decoder_chain_DVBS2_cuda(hc, Fe)
@@ -490,14 +525,23 @@ def main():
                 else:
                     m = Decoder_chain_compact_DVBS2_cuda(hc, Fe, in_kind, SC16 if in_kind == "sc16" else SC8)
                     call = lambda m=m, a=a: m.demodulate_decode(a["sig"], a["x"], a["c1"], a["c2"], V_K_packed=a["V"], n_iter=a["n"], descramble=True)  # noqa: E731
-                clones.append((hc, call, a, (hs, hx, hV, hc1, hc2, hn)))
+                clones.append((hc, call, a, host_bufs[c]))
             torch.cuda.synchronize()
+
+            # one call of clone 0 alone: warm-up, and the length of a call when nothing shares the GPU or the link
+            t_solo = time.perf_counter()
+            clones[0][1]()
+            t_solo = time.perf_counter() - t_solo
 
             def run_clones(n):
                 errors = []
 
                 def work(c):
                     try:
+                        # clones start a fraction of a call apart, as the clones of a replicated StreamPU stage do (each is handed
+                        # its batch when the producer has filled it): the copies of one clone then fall under the kernels of the
+                        # others instead of all clones copying, then all computing, in step
+                        time.sleep(c * t_solo / NC)
                         for _ in range(n):
                             clones[c][1]()
                     except BaseException as e:  # noqa: BLE001 — a clone that stopped early must void the whole measurement
@@ -562,7 +606,7 @@ def main():
             e2e = dict(socks[head])
             e2e["headline_sockets"] = head
             e2e["api"] = API.get(head, head) + "; %d concurrent module clones (host threads) x %d frames per call, one chunk per call" % (
-                NC, e2e["frames_per_step_per_gpu"] // NC)
+                e2e["clones"], e2e["frames_per_step_per_gpu"] // e2e["clones"])
             e2e["vs_device_resident"] = round(e2e["value"] / value, 4)
             e2e["host_numa"] = numa
             e2e["sockets"] = socks
@@ -616,7 +660,7 @@ def main():
         if not args.no_int16:
             try:  # the headline workload through the packed int16 kernel + the int8-LLR socket end to end
                 d = sub(args.workload, "i16", (["--ebn0", str(args.ebn0)] if args.ebn0 is not None else []) +
-                        ["--e2e-sockets", "llr8_packed", "--e2e-clones", str(args.e2e_clones)])
+                        ["--e2e-sockets", "llr8_packed", "--e2e-clones", str(args.e2e_clones)])  # 0 = automatic there too
                 int16 = brief(d)
                 int16["quantizer"] = "Quantizer_pow2 6 bits, 2 fractional (AFF3CT LDPC defaults)"
                 int16["message_passing"] = d["roofline"]["message_passing"]
