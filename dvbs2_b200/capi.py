@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("DVBS2_CUDA_LIB") or os.path.join(HERE, "libdvbs2_cuda
 N_LDPC = 16200
 OK, ERR_INVALID, ERR_CUDA, ERR_TOO_MANY, ERR_NOMEM = 0, -1, -2, -3, -4
 PREC = {"f32": 0, "i16": 1, "i8": 2}
-IQ_FORMAT = {"f32": 0, "f16": 1, "sc16": 2, "sc8": 3}  # dvbs2_iq_format
+IQ_FORMAT = {"f32": 0, "f16": 1, "sc16": 2, "sc8": 3, "sc12": 4}  # dvbs2_iq_format
 MODCOD = {"QPSK-S_8/9": 0, "QPSK-S_3/5": 1, "8PSK-S_3/5": 2, "8PSK-S_8/9": 3, "16APSK-S_8/9": 4}
 
 # every symbol include/dvbs2_cuda.h declares (tests check the library exports all of them)

@@ -1217,13 +1217,13 @@ extern "C"
     {
         TRY(check_frames(h, n_frames));
         if (!Y_N1 || (V_K != nullptr) == (packed != nullptr)) return DVBS2_ERR_INVALID; // exactly one output format
-        if (iq_fmt < DVBS2_IQ_F32 || iq_fmt > DVBS2_IQ_SC8 || !(iq_scale > 0.f)) return DVBS2_ERR_INVALID;
+        if (iq_fmt < DVBS2_IQ_F32 || iq_fmt > DVBS2_IQ_SC12 || !(iq_scale > 0.f)) return DVBS2_ERR_INVALID;
         if (llr8 && h->cfg.precision != DVBS2_PREC_I16) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
         CU(h, cudaSetDevice(h->cfg.device));
         LaunchScope launch_scope(h);
         const size_t inf = llr8 ? (size_t)N_LDPC
-                                : (size_t)2 * (pl_frames ? pl_frame_symbols(h->mc.n_sym) : h->mc.n_sym) * iq_format_bytes(iq_fmt);
+                                : (size_t)(pl_frames ? pl_frame_symbols(h->mc.n_sym) : h->mc.n_sym) * iq_symbol_bytes(iq_fmt);
         const size_t outf = packed ? (size_t)h->mc.K_bch / 8 : (size_t)h->mc.K_bch * sizeof(int32_t);
         TRY(ensure(h, h->in_a, inf * n_frames));
         TRY(ensure(h, h->out_a, outf * n_frames));
@@ -1279,8 +1279,8 @@ extern "C"
     // -------------------------------------------------------- compact socket formats
     size_t dvbs2_cuda_iq_frame_bytes(const dvbs2_cuda_handle* h, int iq_format, int pl_frames)
     {
-        if (!h || iq_format < DVBS2_IQ_F32 || iq_format > DVBS2_IQ_SC8) return 0;
-        return (size_t)2 * (pl_frames ? pl_frame_symbols(h->mc.n_sym) : h->mc.n_sym) * iq_format_bytes(iq_format);
+        if (!h || iq_format < DVBS2_IQ_F32 || iq_format > DVBS2_IQ_SC12) return 0;
+        return (size_t)(pl_frames ? pl_frame_symbols(h->mc.n_sym) : h->mc.n_sym) * iq_symbol_bytes(iq_format);
     }
 
     int dvbs2_cuda_chain_compact(dvbs2_cuda_handle* h, int iq_format, float iq_scale, const float* CP, const void* Y_N1,
@@ -1314,7 +1314,7 @@ extern "C"
     {
         TRY(check_frames(h, n_frames));
         if (!d_Y_N1 || (d_V_K != nullptr) == (d_V_K_packed != nullptr) || (!d_CP && (!d_SIG || !pl_frames))) return DVBS2_ERR_INVALID;
-        if (iq_format < DVBS2_IQ_F32 || iq_format > DVBS2_IQ_SC8 || !(iq_scale > 0.f)) return DVBS2_ERR_INVALID;
+        if (iq_format < DVBS2_IQ_F32 || iq_format > DVBS2_IQ_SC12 || !(iq_scale > 0.f)) return DVBS2_ERR_INVALID;
         CU(h, cudaSetDevice(h->cfg.device));
         return run_chain(h, h->stream, 0, d_CP, (const float*)d_Y_N1, d_CWD_ldpc, d_CWD_bch, d_V_K, d_n_iter, n_frames,
                          d_V_K_packed, descramble, pl_frames != 0, d_CP ? nullptr : d_SIG, iq_format, iq_scale);

@@ -48,6 +48,13 @@ load_sym(const DemapLaunch& a, size_t i)
         return __fmul_rn((float)__ldg(reinterpret_cast<const int16_t*>(a.sym) + i), a.iq_scale);
     else if constexpr (FMT == 3)
         return __fmul_rn((float)__ldg(reinterpret_cast<const int8_t*>(a.sym) + i), a.iq_scale);
+    else if constexpr (FMT == 4)
+    { // component i of symbol i / 2: three bytes per symbol, I in bits 0..11 and Q in bits 12..23 of the little-endian word
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(a.sym) + (i >> 1) * 3;
+        const uint32_t b1 = __ldg(p + 1);
+        const uint32_t v = (i & 1) ? ((b1 >> 4) | ((uint32_t)__ldg(p + 2) << 4)) : ((uint32_t)__ldg(p) | ((b1 & 0xfu) << 8));
+        return __fmul_rn((float)(((int)(v << 20)) >> 20), a.iq_scale);
+    }
     else
         return __ldg(a.sym + i);
 }
@@ -377,6 +384,7 @@ launch_demap_frames(const DemapLaunch& a, float* llr, int deinterleave, cudaStre
         case 1: demap_frames_kernel<BPS, 1><<<grid, 256, 0, s>>>(a, llr, deinterleave); break;                         \
         case 2: demap_frames_kernel<BPS, 2><<<grid, 256, 0, s>>>(a, llr, deinterleave); break;                         \
         case 3: demap_frames_kernel<BPS, 3><<<grid, 256, 0, s>>>(a, llr, deinterleave); break;                         \
+        case 4: demap_frames_kernel<BPS, 4><<<grid, 256, 0, s>>>(a, llr, deinterleave); break;                         \
         default: demap_frames_kernel<BPS, 0><<<grid, 256, 0, s>>>(a, llr, deinterleave); break;                        \
     }
     switch (a.bps)
@@ -403,6 +411,7 @@ demap_to_var_launch(const DemapLaunch& a, void* var, cudaStream_t s)
         case 1: demap_to_var_kernel<BPS, R, NF, 1><<<grid, WARPS * 32, 0, s>>>(a, (R*)var); break;
         case 2: demap_to_var_kernel<BPS, R, NF, 2><<<grid, WARPS * 32, 0, s>>>(a, (R*)var); break;
         case 3: demap_to_var_kernel<BPS, R, NF, 3><<<grid, WARPS * 32, 0, s>>>(a, (R*)var); break;
+        case 4: demap_to_var_kernel<BPS, R, NF, 4><<<grid, WARPS * 32, 0, s>>>(a, (R*)var); break;
         default: demap_to_var_kernel<BPS, R, NF, 0><<<grid, WARPS * 32, 0, s>>>(a, (R*)var); break;
     }
     count_launch();
@@ -459,6 +468,7 @@ launch_estimate(const DemapLaunch& a, int K_bch, float* sigma, float* ebn0, floa
         case 1: estimate_kernel<1><<<blocks, 128, 0, s>>>(a, K_bch, sigma, ebn0, esn0); break;
         case 2: estimate_kernel<2><<<blocks, 128, 0, s>>>(a, K_bch, sigma, ebn0, esn0); break;
         case 3: estimate_kernel<3><<<blocks, 128, 0, s>>>(a, K_bch, sigma, ebn0, esn0); break;
+        case 4: estimate_kernel<4><<<blocks, 128, 0, s>>>(a, K_bch, sigma, ebn0, esn0); break;
         default: estimate_kernel<0><<<blocks, 128, 0, s>>>(a, K_bch, sigma, ebn0, esn0); break;
     }
     count_launch();

@@ -158,14 +158,14 @@ struct DemapLaunch
     int quant_dec, quant_bits; // for integer outputs
     int pl_sym;                // > 0: sym holds whole PL frames [frames][2*pl_sym]; the payload symbols are picked out in place
                                // (Framer::remove_plh fused into the read side), 0: sym holds XFEC frames
-    int sym_fmt;               // wire format of sym (dvbs2_iq_format): 0 float, 1 IEEE half, 2 int16 * iq_scale, 3 int8 * iq_scale
+    int sym_fmt;               // wire format of sym (dvbs2_iq_format): 0 float, 1 IEEE half, 2 int16 * iq_scale, 3 int8 * iq_scale, 4 packed 12-bit * iq_scale
     float iq_scale;            // value of one LSB for the integer formats
 };
-// bytes per I or Q component of a dvbs2_iq_format
+// bytes per complex symbol (I and Q) of a dvbs2_iq_format
 __host__ __device__ inline int
-iq_format_bytes(int fmt)
+iq_symbol_bytes(int fmt)
 {
-    return fmt == 0 ? 4 : fmt == 3 ? 1 : 2;
+    return fmt == 0 ? 8 : fmt == 3 ? 2 : fmt == 4 ? 3 : 4;
 }
 // PL frame geometry (src/common/Module/Framer/Framer.hxx:36-38,330-343; src/common/Factory/DVBS2/DVBS2.cpp:352-355): 90-symbol
 // header, then the payload with a 36-symbol pilot block after every 1440 payload symbols (n_sym / 1440 blocks in all)

@@ -267,7 +267,7 @@ class Decoder_chain_DVBS2_cuda(_Module):
             None if n_iter is None else _dev_ptr(n_iter, "int32", F, "n_iter"), int(bool(descramble)), F))
 
 
-IQ_DTYPE = {"f32": np.float32, "f16": np.float16, "sc16": np.int16, "sc8": np.int8}
+IQ_DTYPE = {"f32": np.float32, "f16": np.float16, "sc16": np.int16, "sc8": np.int8, "sc12": np.uint8}  # sc12: 3 bytes per symbol
 
 
 def iq_pack(Y_N1, iq_format, iq_scale=1.0):
@@ -278,9 +278,13 @@ def iq_pack(Y_N1, iq_format, iq_scale=1.0):
         return Y_N1
     if iq_format == "f16":
         return Y_N1.astype(np.float16)
-    lim = 32767 if iq_format == "sc16" else 127
+    lim = {"sc16": 32767, "sc8": 127, "sc12": 2047}[iq_format]
     q = Y_N1 * (np.float32(1.0) / np.float32(iq_scale))  # same two float operations as IQ_packer<Q> (Adaptor_DVBS2_cuda.hpp)
     q = np.sign(q) * np.floor(np.abs(q) + np.float32(0.5))
+    if iq_format == "sc12":  # [..., 2 n] components -> [..., 3 n] bytes: I = bits 0..11, Q = bits 12..23 of a little-endian word
+        v = np.clip(q, -lim, lim).astype(np.int32) & 0xfff
+        w = v[..., 0::2] | (v[..., 1::2] << 12)
+        return np.stack([w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff], axis=-1).astype(np.uint8).reshape(*w.shape[:-1], -1)
     return np.clip(q, -lim, lim).astype(IQ_DTYPE[iq_format])
 
 
@@ -288,6 +292,13 @@ def iq_unpack(Y, iq_format, iq_scale=1.0):
     """wire format -> the float samples the device computes with ((float)x * scale, one rounded multiply)"""
     if iq_format in ("f32", "f16"):
         return np.asarray(Y).astype(np.float32)
+    if iq_format == "sc12":
+        b = np.asarray(Y, np.uint8).astype(np.int32)
+        b = b.reshape(*b.shape[:-1], -1, 3)
+        w = b[..., 0] | (b[..., 1] << 8) | (b[..., 2] << 16)
+        comp = np.stack([w & 0xfff, (w >> 12) & 0xfff], axis=-1).reshape(*w.shape[:-1], -1)
+        comp = (comp ^ 0x800) - 0x800  # sign-extend 12 bits
+        return comp.astype(np.float32) * np.float32(iq_scale)
     return np.asarray(Y).astype(np.float32) * np.float32(iq_scale)
 
 
@@ -302,6 +313,8 @@ class Decoder_chain_compact_DVBS2_cuda(_Module):
         self.K = handle.info["K_bch"]
         self.iq_format, self.iq_scale, self.pl_frames = iq_format, float(iq_scale), bool(pl_frames)
         self.N_fil = (handle.lib.dvbs2_cuda_pl_frame_size(handle._h) if pl_frames else 2 * handle.info["n_sym"])
+        if iq_format == "sc12":
+            self.N_fil = self.N_fil // 2 * 3  # bytes per frame: the socket is a byte array
         assert handle.lib.dvbs2_cuda_iq_frame_bytes(handle._h, capi.IQ_FORMAT[iq_format], int(pl_frames)) == \
             self.N_fil * np.dtype(IQ_DTYPE[iq_format]).itemsize
 

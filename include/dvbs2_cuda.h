@@ -194,7 +194,9 @@ extern "C"
         DVBS2_IQ_F32 = 0,  /* float I, float Q: the reference socket (8 B / symbol)                                    */
         DVBS2_IQ_F16 = 1,  /* IEEE binary16 I/Q (4 B / symbol); converted exactly to float on the device               */
         DVBS2_IQ_SC16 = 2, /* int16 I/Q x iq_scale (4 B / symbol), the USRP/UHD "sc16" wire format                      */
-        DVBS2_IQ_SC8 = 3   /* int8 I/Q x iq_scale (2 B / symbol), UHD "sc8"                                             */
+        DVBS2_IQ_SC8 = 3,  /* int8 I/Q x iq_scale (2 B / symbol), UHD "sc8"                                             */
+        DVBS2_IQ_SC12 = 4  /* 12-bit two's-complement I and Q x iq_scale in 3 bytes per symbol (the resolution of UHD's "sc12"
+                            * wire format): little-endian 24-bit word, I = bits 0..11, Q = bits 12..23                    */
     } dvbs2_iq_format;
     /* bytes of one frame's symbols in that format (XFEC frame, or PL frame when pl_frames != 0) */
     size_t dvbs2_cuda_iq_frame_bytes(const dvbs2_cuda_handle* h, int iq_format, int pl_frames);

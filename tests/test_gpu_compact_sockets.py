@@ -21,7 +21,7 @@ def _chain_f32(modcod, cp, sym, F):
 
 
 @pytest.mark.parametrize("modcod,ebn0", [("QPSK-S_8/9", 4.0), ("8PSK-S_3/5", 3.9), ("16APSK-S_8/9", 7.8)])
-@pytest.mark.parametrize("fmt,scale", [("sc16", 1.0 / 8192), ("sc8", 1.0 / 40), ("f16", 1.0)])
+@pytest.mark.parametrize("fmt,scale", [("sc16", 1.0 / 8192), ("sc8", 1.0 / 40), ("f16", 1.0), ("sc12", 1.0 / 512)])
 def test_compact_symbol_formats_equal_float_sockets_on_the_same_samples(oracle, modcod, ebn0, fmt, scale):
     from dvbs2_b200 import Decoder_chain_compact_DVBS2_cuda, Handle
     from dvbs2_b200.modules import iq_pack, iq_unpack
@@ -29,7 +29,7 @@ def test_compact_symbol_formats_equal_float_sockets_on_the_same_samples(oracle, 
     F, K = 70, MODCODS[modcod]["K_bch"]
     s = synth_frames(oracle, modcod, F, ebn0, seed=31)
     wire = np.ascontiguousarray(iq_pack(s["rx"], fmt, scale))
-    assert wire.nbytes * (4 if fmt == "sc8" else 2) == s["rx"].nbytes
+    assert wire.nbytes * {"sc8": 8, "sc12": 8, "sc16": 4, "f16": 4}[fmt] == s["rx"].nbytes * {"sc8": 2, "sc12": 3, "sc16": 2, "f16": 2}[fmt]
     want = _chain_f32(modcod, s["sigma"], iq_unpack(wire, fmt, scale), F)  # float sockets, same sample values
     h = Handle(modcod=modcod, n_frames=F)
     m = Decoder_chain_compact_DVBS2_cuda(h, F, fmt, scale)
