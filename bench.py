@@ -427,14 +427,15 @@ def main():
             # one call of a clone = one wave of the LDPC kernel (every launch fills the machine; the copies of one clone overlap
             # the kernels of the others, so calls are not chunked).  The reference's int32-per-bit sockets need 14 GB of pinned
             # memory per wave and clone: half a wave there when eight ranks share one host.
-            # Call shape.  The reference's float sockets: NC clones x one wave per call (their staging buffers leave no room for
-            # more).  Compact input sockets: TWO clones x the whole device-resident batch per call — every LDPC launch then has the
-            # three waves that make the device-resident figure (single-wave launches lose 15 % to their tails: 16.7 against
-            # 19.7 Gbit/s), and the copies of one clone still lie under the kernels of the other.  --e2e-frames / --e2e-clones
-            # given explicitly pin the shape.
+            # Call shape.  NC clones x one wave per call, except for 8-bit samples: TWO clones x the whole device-resident batch
+            # per call — every LDPC launch then has the three waves that make the device-resident figure (single-wave launches lose
+            # 15 % to their tails: 16.7 against 19.7 Gbit/s).  That only pays while the H2D copy of a call is short: the copy engine
+            # gets 20-35 GB/s, not the link's 55, while the LDPC kernel of the other clone saturates HBM (measured,
+            # scripts/gpu_r2_sc12.sh: three-wave calls give 14.4 / 15.6 / 17.8 Gbit/s with sc16 / sc12 / sc8 against 15.9 / - / 15.5
+            # for one-wave calls).  --e2e-frames / --e2e-clones given explicitly pin the shape.
             NC = NC0
             hpf = {"f32": 195e3, "i16": 118e3, "i8": 80e3}["i16" if in_kind == "llr8" else args.prec]  # handle bytes per frame (measured)
-            big = allow_big and in_kind != "f32" and args.e2e_frames == 0 and not args.e2e_clones_given
+            big = allow_big and in_kind == "sc8" and args.e2e_frames == 0 and not args.e2e_clones_given
             if big:
                 need = 2 * F * (hpf + ({"sc16": 4, "sc12": 3, "sc8": 2}.get(in_kind, 0) * n_sym or N_LDPC) + K_bch // 8 + 64)
                 big = need < 0.97 * torch.cuda.mem_get_info(dev)[0]
