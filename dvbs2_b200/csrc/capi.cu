@@ -8,6 +8,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only; ranges cost nothing unless a profiler is attached
 
 #include "../../include/dvbs2_cuda.h"
 #include "kernels.h"
@@ -143,6 +144,17 @@ fail_cuda(dvbs2_cuda_handle* h, cudaError_t e, const char* what)
     return e == cudaErrorMemoryAllocation ? DVBS2_ERR_NOMEM : DVBS2_ERR_CUDA;
 }
 
+// NVTX range around a C-ABI call / a stage of the chain as it is queued: the hook a timeline profiler (Nsight Systems) needs to
+// attribute kernels and copies to the StreamPU task that caused them (the reference's tasks carry timers; these are
+// the device-side counterpart next to dvbs2_cuda_get_timers)
+struct NvtxRange
+{
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 // credits the kernels launched by this thread during an API call to the handle the call works on
 struct LaunchScope
 {
@@ -221,6 +233,8 @@ prof_collect(dvbs2_cuda_handle* h)
 int
 prof_mark(dvbs2_cuda_handle* h, cudaStream_t s, int stage)
 {
+    static const char* const names[] = { "dvbs2:demap", "dvbs2:ldpc", "dvbs2:bch", "dvbs2:unpack", "dvbs2:pack" };
+    nvtxMarkA(stage >= 0 && stage < P_COUNT ? names[stage] : "dvbs2:end"); // where the stage's launches begin on the host timeline
     if (!h->profiling) return DVBS2_OK;
     if (h->n_marks == PROF_MAX_MARKS) TRY(prof_collect(h));
     if (h->n_marks == h->marks.size())
@@ -1151,6 +1165,7 @@ extern "C"
         TRY(check_frames(h, n_frames));
         if (!Y_N || !V_K) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
+        NvtxRange nvtx_range("dvbs2_cuda_ldpc_decode_siho");
         CU(h, cudaSetDevice(h->cfg.device));
         LaunchScope launch_scope(h);
         const size_t inf = (size_t)N_LDPC * h->elt, outf = (size_t)h->mc.N_bch * sizeof(int32_t);
@@ -1182,6 +1197,7 @@ extern "C"
         TRY(check_frames(h, n_frames));
         if (!Y_N || !V_K) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
+        NvtxRange nvtx_range("dvbs2_cuda_bch_decode_hiho");
         CU(h, cudaSetDevice(h->cfg.device));
         LaunchScope launch_scope(h);
         const size_t inf = (size_t)h->mc.N_bch * sizeof(int32_t), outf = (size_t)h->mc.K_bch * sizeof(int32_t);
@@ -1220,6 +1236,7 @@ extern "C"
         if (iq_fmt < DVBS2_IQ_F32 || iq_fmt > DVBS2_IQ_SC12 || !(iq_scale > 0.f)) return DVBS2_ERR_INVALID;
         if (llr8 && h->cfg.precision != DVBS2_PREC_I16) return DVBS2_ERR_INVALID;
         if (n_frames == 0) return DVBS2_OK;
+        NvtxRange nvtx_range(llr8 ? "dvbs2_cuda_decode_llr8" : pl_frames ? "dvbs2_cuda_rx_chain" : "dvbs2_cuda_chain");
         CU(h, cudaSetDevice(h->cfg.device));
         LaunchScope launch_scope(h);
         const size_t inf = llr8 ? (size_t)N_LDPC
