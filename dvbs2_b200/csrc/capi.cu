@@ -256,6 +256,8 @@ prof_mark(dvbs2_cuda_handle* h, cudaStream_t s, int stage)
 int
 call_nf(const dvbs2_cuda_handle* h, int n_frames)
 {
+    // int16: four frames per lane (packed pairs), except for the small calls that go to the cooperative kernel (one per lane)
+    if (h->cfg.precision == DVBS2_PREC_I16 && h->coop_max > 0 && n_frames <= h->coop_max) return 1;
     if (h->cfg.precision != DVBS2_PREC_F32) return h->nf;
     if (h->nf_cfg) return h->nf_cfg;
     return n_frames <= h->n_sms * LDPC_WARPS * 32 ? 1 : 2;
@@ -267,7 +269,8 @@ call_nf(const dvbs2_cuda_handle* h, int n_frames)
 bool
 call_coop(const dvbs2_cuda_handle* h, int n_frames, int nf)
 {
-    return h->cfg.precision == DVBS2_PREC_F32 && nf == 1 && h->coop_max > 0 && n_frames <= h->coop_max;
+    return (h->cfg.precision == DVBS2_PREC_F32 || h->cfg.precision == DVBS2_PREC_I16) && nf == 1 && h->coop_max > 0 &&
+           n_frames <= h->coop_max;
 }
 
 // `first_frame` is a multiple of the group size 32 * nf; per-frame offsets follow from the layouts in kernels.h
@@ -442,7 +445,9 @@ run_ldpc_core(dvbs2_cuda_handle* h, cudaStream_t s, int first_frame, int n_frame
     LdpcLaunch a = ldpc_args(h, s, first_frame, n_frames, d_cwd, d_nit, nf0);
     if (call_coop(h, n_frames, nf0))
     {
-        CU(h, launch_ldpc_decode_coop(a, s));
+        // the cooperative kernel keeps its own check-state layout (one round, nothing else reads it): per-chunk offset in its units
+        a.cn = (uint4*)((char*)h->cn.p + (size_t)first_frame * h->mc.M * ldpc_coop_state_bytes(h->cfg.precision, h->mc.d_info));
+        CU(h, launch_ldpc_decode_coop(a, h->cfg.precision, s));
         return DVBS2_OK;
     }
     const bool multi = h->rounds > 1 && h->ext_cap > 0 && h->cfg.early_stop && h->cfg.n_ite >= 4 && a.n_groups >= 2;
@@ -923,7 +928,10 @@ extern "C"
         const size_t FE = F + h->ext_cap;                    // var / cn slots
         const size_t FS = F + h->ext_slots, GS = FS / 32;    // hd / out_hd / bookkeeping slots
         int rc;
-        if ((rc = ensure(h, h->var, FE * N_LDPC * h->elt)) || (rc = ensure(h, h->cn, FE * mc.M * h->cn_bytes)) ||
+        if ((rc = ensure(h, h->var, FE * N_LDPC * h->elt)) || (rc = ensure(h, h->cn, std::max(FE * mc.M * h->cn_bytes,
+                                          // small calls of the cooperative kernel: its own (wider for int16) state per frame
+                                          std::min(F, (size_t)std::max(h->coop_max, 0) + 128) * mc.M *
+                                            (cfg->precision == DVBS2_PREC_I8 ? 0 : ldpc_coop_state_bytes(cfg->precision, mc.d_info))))) ||
             (rc = ensure(h, h->hd, GS * N_LDPC * 4)) || (rc = ensure(h, h->out_hd, GS * N_LDPC * 4)) ||
             (rc = ensure(h, h->surv_mask, GS * 4 + 4)) || (rc = ensure(h, h->surv_iters, FS * 4 + 4)) ||
             (rc = ensure(h, h->dst_base, GS * 4 + 4)) || (rc = ensure(h, h->src_of_dst, FS * 4 + 4)) ||

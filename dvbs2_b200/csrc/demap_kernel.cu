@@ -194,6 +194,12 @@ struct LaneVec<float, 2>
     __device__ static T make(const float* x) { return make_float2(x[0], x[1]); }
 };
 template<>
+struct LaneVec<int16_t, 1> // one frame per lane: the cooperative small-batch LDPC kernel
+{
+    using T = int16_t;
+    __device__ static T make(const int16_t* x) { return x[0]; }
+};
+template<>
 struct LaneVec<int16_t, 4>
 {
     using T = uint2;
@@ -421,8 +427,8 @@ template<int BPS>
 static cudaError_t
 demap_to_var_bps(const DemapLaunch& a, void* var, int precision, int nf, cudaStream_t s)
 {
-    // the group width follows the precision: 1 or 2 (chosen per call) for float, 4 for int16 and int8
-    if (precision == 0 ? (nf != 1 && nf != 2) : nf != 4) return cudaErrorInvalidValue;
+    // the group width follows the precision: 1 or 2 (chosen per call) for float, 4 (or 1: small batches) for int16, 4 for int8
+    if (precision == 0 ? (nf != 1 && nf != 2) : precision == 1 ? (nf != 1 && nf != 4) : nf != 4) return cudaErrorInvalidValue;
     switch (precision)
     {
         case 0:
@@ -431,7 +437,12 @@ demap_to_var_bps(const DemapLaunch& a, void* var, int precision, int nf, cudaStr
             else
                 demap_to_var_launch<BPS, float, 2>(a, var, s);
             break;
-        case 1: demap_to_var_launch<BPS, int16_t, 4>(a, var, s); break;
+        case 1:
+            if (nf == 1)
+                demap_to_var_launch<BPS, int16_t, 1>(a, var, s);
+            else
+                demap_to_var_launch<BPS, int16_t, 4>(a, var, s);
+            break;
         case 2: demap_to_var_launch<BPS, int8_t, 4>(a, var, s); break;
         default: return cudaErrorInvalidValue;
     }

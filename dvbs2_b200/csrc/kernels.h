@@ -107,7 +107,8 @@ int ldpc_later_frames_per_lane(int precision, int preferred);
 int ldpc_frames_per_lane(int precision); // NF: 2 (f32, i16), 4 (i8)
 cudaError_t launch_ldpc_decode(const LdpcLaunch& a, int precision, cudaStream_t s);
 // float, 32-frame groups, a whole CTA per group (small batches): same results, one round
-cudaError_t launch_ldpc_decode_coop(const LdpcLaunch& a, cudaStream_t s);
+cudaError_t launch_ldpc_decode_coop(const LdpcLaunch& a, int precision, cudaStream_t s); // float or int16, one frame per lane
+int ldpc_coop_state_bytes(int precision, int d_info); // check state of that kernel per (check, frame)
 // smallest distance (in checks) between two checks sharing an information variable that the cooperative kernel tolerates
 int ldpc_coop_min_reuse();
 int ldpc_state_words(int d_info); // 32-bit words of compressed check state per (check, frame / int16 pair): 3 for degree <= 11, else 4

@@ -60,6 +60,7 @@ struct Arith<float>
     __device__ static C normalize(C v, float f, int) { return __fmul_rn(v, f); } // Update_rule_NMS.hxx:41-46
     __device__ static C with_sign(C m, unsigned s) { return __uint_as_float(__float_as_uint(m) | (s << 31)); }
     __device__ static unsigned raw(C t) { return __float_as_uint(t); } // bit 31 = neg(t)
+    __device__ static C from_bits(unsigned w) { return __uint_as_float(w); } // inverse of raw()
     // magnitude m >= 0 with the sign held in bit 31 of w
     __device__ static C apply_sign(C m, unsigned w) { return __uint_as_float(__float_as_uint(m) | (w & 0x80000000u)); }
     __device__ static unsigned pack(C a, C b, unsigned& hi)
@@ -101,6 +102,7 @@ struct ArithInt
     }
     __device__ static C with_sign(C m, unsigned s) { return wrap(s ? -m : m); }
     __device__ static unsigned raw(C t) { return (unsigned)t; } // bit 31 = neg(t): values are sign-extended ints
+    __device__ static C from_bits(unsigned w) { return (int)w; }  // inverse of raw()
     __device__ static C apply_sign(C m, unsigned w) { return wrap((int)w < 0 ? -m : m); }
     __device__ static unsigned pack(C a, C b, unsigned& hi)
     {
@@ -796,14 +798,58 @@ mbar_wait_acquire(uint64_t* bar, unsigned parity)
     } while (!ok);
 }
 
-template<int DI>
+// Compressed check state of the cooperative kernel (one frame per lane, its own layout: the kernel runs one round, nothing else
+// reads it).  float: the words of ldpc_decode_kernel (STATE_WORDS<DI>).  int16_t: three words per (check, frame) — both output
+// magnitudes in one, then the sign bits and the "== min1" bits (sharing a word when the check has at most 16 edges).
+template<typename R, int DI>
+struct CoopState
+{
+    using A = Arith<R>;
+    using C = typename A::C;
+    static constexpr bool FLT = sizeof(R) == 4;
+    static constexpr int D = DI + 2;
+    static constexpr int SW = FLT ? STATE_WORDS<DI> : 3;
+    static __device__ __forceinline__ void decode(const uint4 st, C& o1, C& o2, unsigned& osg, unsigned& oeq)
+    {
+        if constexpr (FLT)
+        {
+            A::unpack(st.x, st.y, o1, o2);
+            if constexpr (SW == 4)
+                osg = st.z, oeq = st.w;
+            else
+                osg = st.z & 0xffffu, oeq = st.z >> 16;
+        }
+        else
+        {
+            A::unpack(st.x, 0u, o1, o2);
+            if constexpr (D > 16)
+                osg = st.y, oeq = st.z;
+            else
+                osg = st.y & 0xffffu, oeq = st.y >> 16;
+        }
+    }
+    static __device__ __forceinline__ uint4 encode(const C c1, const C c2, const unsigned nsg, const unsigned neq)
+    {
+        unsigned hi;
+        const unsigned lo = A::pack(c1, c2, hi);
+        if constexpr (FLT)
+            return SW == 4 ? make_uint4(lo, hi, nsg, neq) : make_uint4(lo, hi, nsg | (neq << 16), 0u);
+        else
+            return D > 16 ? make_uint4(lo, nsg, neq, 0u) : make_uint4(lo, nsg | (neq << 16), 0u, 0u);
+    }
+};
+
+template<typename R, int DI>
 __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(const LdpcLaunch a)
 {
-    using A = Arith<float>;
+    static_assert(sizeof(R) == 4 || sizeof(R) == 2, "float (the dvbs2 binaries) and int16_t (AFF3CT's functional fixed-point path)");
+    using A = Arith<R>;
+    using C = typename A::C;
+    using ST = CoopState<R, DI>;
     constexpr int NWK = COOP_WORKERS;
     constexpr int D = DI + 2;        // edges per check incl. the two parity edges (bit DI = in, DI+1 = out)
     constexpr int IW = (DI + 1) / 2; // u32 words per index row
-    constexpr unsigned VB = 32 * sizeof(float);
+    constexpr unsigned VB = 32 * sizeof(R);
     constexpr int SLOT = 10 * 32;    // words per worker slot: 5 posted + 5 answered, 32 lanes each
 
     extern __shared__ uint32_t smem[];
@@ -837,9 +883,8 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
         if (g >= n_groups) break;
 
         char* __restrict__ vbytes = (char*)a.var + (size_t)g * N_LDPC * VB;
-        const unsigned loff = lane * (unsigned)sizeof(float);
-        constexpr int SW = STATE_WORDS<DI>;
-        using SIO = StateIO<SW>;
+        const unsigned loff = lane * (unsigned)sizeof(R);
+        using SIO = StateIO<ST::SW>;
         uint32_t* __restrict__ cn = reinterpret_cast<uint32_t*>(a.cn) + (size_t)g * SIO::group_words(M, 1) + SIO::lane_offset(lane);
         uint32_t* __restrict__ hd = a.hd + (size_t)g * N_LDPC;
         uint32_t* __restrict__ out_hd = a.out_hd + (size_t)g * N_LDPC;
@@ -857,8 +902,8 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
                 // ---- the chain: x = var[K+c-1] after check c-1, per lane (= frame).  The words posted for check c+1 are
                 //      fetched before check c is computed: they do not depend on the chain, and their shared-memory latency
                 //      (and the barrier test) then lie beside the dependent instructions instead of between them.
-                float x = FLT_MAX;
-                float n_m1, n_m2, n_tout, n_msg;
+                C x = A::max_value();
+                C n_m1, n_m2, n_tout, n_msg;
                 unsigned n_sa;
                 auto fetch = [&](int c) {
                     const int u = c % NWK;
@@ -866,33 +911,33 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
                     const unsigned par = __shfl_sync(FULL, visits, u) & 1u;
                     if (lane == u) visits++;
                     mbar_wait_acquire(s_posted + u, par);
-                    n_m1 = __uint_as_float(sl[0 * 32]), n_m2 = __uint_as_float(sl[1 * 32]);
+                    n_m1 = A::from_bits(sl[0 * 32]), n_m2 = A::from_bits(sl[1 * 32]);
                     n_sa = sl[2 * 32];
-                    n_tout = __uint_as_float(sl[3 * 32]);
-                    n_msg = __uint_as_float(sl[4 * 32]);
+                    n_tout = A::from_bits(sl[3 * 32]);
+                    n_msg = A::from_bits(sl[4 * 32]);
                 };
                 fetch(0);
 #pragma unroll 1
                 for (int c = 0; c < M; c++)
                 {
                     uint32_t* sl = s_slot + (c % NWK) * SLOT + lane;
-                    float m1 = n_m1, m2 = n_m2;
+                    C m1 = n_m1, m2 = n_m2;
                     unsigned sa = n_sa;
-                    const float t_out = n_tout, msg_in = n_msg;
+                    const C t_out = n_tout, msg_in = n_msg;
                     if (c + 1 < M) fetch(c + 1);
-                    const float ti = c == 0 ? FLT_MAX : A::sub(x, msg_in); // check 0 has no incoming chain edge
-                    const float ab = fabsf(ti);
-                    sa ^= __float_as_uint(ti);
-                    m2 = fminf(m2, fmaxf(ab, m1));
-                    m1 = fminf(m1, ab);
-                    const float c1 = fmaxf(0.f, A::normalize(m2, a.norm, a.k8)); // Update_rule_NMS.hxx:100-106
-                    const float c2 = fmaxf(0.f, A::normalize(m1, a.norm, a.k8));
-                    const bool e = fabsf(t_out) == m1;
-                    x = A::add(t_out, A::apply_sign(e ? c1 : c2, sa ^ __float_as_uint(t_out))); // var[K+c]
-                    sl[5 * 32] = __float_as_uint(ti);
-                    sl[6 * 32] = __float_as_uint(m1);
-                    sl[7 * 32] = __float_as_uint(c1);
-                    sl[8 * 32] = __float_as_uint(c2);
+                    const C ti = c == 0 ? A::max_value() : A::sub(x, msg_in); // check 0 has no incoming chain edge
+                    const C ab = A::absv(ti);
+                    sa ^= A::raw(ti);
+                    m2 = A::vmin(m2, A::vmax(ab, m1));
+                    m1 = A::vmin(m1, ab);
+                    const C c1 = A::vmax((C)0, A::normalize(m2, a.norm, a.k8)); // Update_rule_NMS.hxx:100-106
+                    const C c2 = A::vmax((C)0, A::normalize(m1, a.norm, a.k8));
+                    const bool e = A::absv(t_out) == m1;
+                    x = A::add(t_out, A::apply_sign(e ? c1 : c2, sa ^ A::raw(t_out))); // var[K+c]
+                    sl[5 * 32] = A::raw(ti);
+                    sl[6 * 32] = A::raw(m1);
+                    sl[7 * 32] = A::raw(c1);
+                    sl[8 * 32] = A::raw(c2);
                     sl[9 * 32] = sa;
                     __syncwarp();
                     if (lane == 0) mbar_arrive_release(s_answered + (c % NWK));
@@ -900,7 +945,7 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
             }
             else
             {
-                float v[DI + 1]; // information variables of the check, then var[K+c]
+                C v[DI + 1]; // information variables of the check, then var[K+c]
                 uint4 st;
                 auto issue = [&](int c) {
                     const uint32_t* row = s_idx + c * IW;
@@ -908,11 +953,10 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
                     for (int i = 0; i < DI; i++)
                     {
                         const unsigned vi = (row[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-                        v[i] = __ldcg(reinterpret_cast<const float*>(vbytes + (vi * VB + loff)));
+                        v[i] = (C)__ldcg(reinterpret_cast<const R*>(vbytes + (vi * VB + loff)));
                     }
-                    v[DI] = __ldcg(reinterpret_cast<const float*>(vbytes + ((unsigned)(K + c) * VB + loff)));
+                    v[DI] = (C)__ldcg(reinterpret_cast<const R*>(vbytes + ((unsigned)(K + c) * VB + loff)));
                     st = have_state ? SIO::load(cn, (size_t)c) : make_uint4(0u, 0u, 0u, 0u);
-                    if constexpr (SW == 3) st.w = st.z >> 16, st.z &= 0xffffu;
                 };
                 uint32_t* sl = s_slot + w * SLOT + lane;
                 if (w < M) issue(w);
@@ -922,39 +966,40 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
                     const uint32_t* row = s_idx + c * IW;
                     const uint32_t lastm = s_last[c];
                     // ---- every edge but the incoming chain edge (pass 1 of Update_rule_MS.hxx:57-67 on D - 1 edges)
-                    const float o1 = __uint_as_float(st.x), o2 = __uint_as_float(st.y);
-                    const unsigned osg = st.z, oeq = st.w;
-                    float t[D];
+                    C o1, o2;
+                    unsigned osg, oeq;
+                    ST::decode(st, o1, o2, osg, oeq);
+                    C t[D];
                     unsigned sa = 0;
-                    float m1 = FLT_MAX, m2 = FLT_MAX;
+                    C m1 = A::max_value(), m2 = A::max_value();
 #pragma unroll
                     for (int i = 0; i < D; i++)
                     {
                         if (i == DI) continue;
                         const int b = D - 1 - i;
-                        const float mag = (oeq & (1u << b)) ? o1 : o2;
-                        const float ti = A::sub(v[i < DI ? i : DI], A::apply_sign(mag, osg << (31 - b)));
+                        const C mag = (oeq & (1u << b)) ? o1 : o2;
+                        const C ti = A::sub(v[i < DI ? i : DI], A::apply_sign(mag, osg << (31 - b)));
                         t[i] = ti;
-                        const float ab = fabsf(ti);
-                        sa ^= __float_as_uint(ti);
-                        m2 = fminf(m2, fmaxf(ab, m1));
-                        m1 = fminf(m1, ab);
+                        const C ab = A::absv(ti);
+                        sa ^= A::raw(ti);
+                        m2 = A::vmin(m2, A::vmax(ab, m1));
+                        m1 = A::vmin(m1, ab);
                     }
                     // the chain edge is edge DI: bit D - 1 - DI = 1 of the state words
-                    sl[0 * 32] = __float_as_uint(m1);
-                    sl[1 * 32] = __float_as_uint(m2);
+                    sl[0 * 32] = A::raw(m1);
+                    sl[1 * 32] = A::raw(m2);
                     sl[2 * 32] = sa;
-                    sl[3 * 32] = __float_as_uint(t[DI + 1]);
-                    sl[4 * 32] = __float_as_uint(A::apply_sign((oeq & 2u) ? o1 : o2, osg << 30));
+                    sl[3 * 32] = A::raw(t[DI + 1]);
+                    sl[4 * 32] = A::raw(A::apply_sign((oeq & 2u) ? o1 : o2, osg << 30));
                     __syncwarp();
                     if (lane == 0) mbar_arrive_release(s_posted + w);
                     if (c + NWK < M) issue(c + NWK);
 
                     mbar_wait_acquire(s_answered + w, n_turns & 1u);
                     n_turns++;
-                    t[DI] = __uint_as_float(sl[5 * 32]);
-                    m1 = __uint_as_float(sl[6 * 32]);
-                    const float c1 = __uint_as_float(sl[7 * 32]), c2 = __uint_as_float(sl[8 * 32]);
+                    t[DI] = A::from_bits(sl[5 * 32]);
+                    m1 = A::from_bits(sl[6 * 32]);
+                    const C c1 = A::from_bits(sl[7 * 32]), c2 = A::from_bits(sl[8 * 32]);
                     sa = sl[9 * 32];
 
                     // ---- new messages (Update_rule_MS.hxx:82-92, ...layered.hxx:198-203)
@@ -962,10 +1007,10 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
 #pragma unroll
                     for (int i = 0; i < D; i++)
                     {
-                        const float tt = t[i];
-                        const bool e = fabsf(tt) == m1;
-                        const unsigned xs = sa ^ __float_as_uint(tt); // bit 31: sign of the new message
-                        const float nv = A::add(tt, A::apply_sign(e ? c1 : c2, xs));
+                        const C tt = t[i];
+                        const bool e = A::absv(tt) == m1;
+                        const unsigned xs = sa ^ A::raw(tt); // bit 31: sign of the new message
+                        const C nv = A::add(tt, A::apply_sign(e ? c1 : c2, xs));
                         if (e) neq |= 1u << (D - 1 - i);
                         nsg |= (xs >> 31) << (D - 1 - i);
                         unsigned vi;
@@ -987,17 +1032,14 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) ldpc_decode_coop_kernel(co
                             vi = K + c;
                             ballot = true;
                         }
-                        if (mine) __stcg(reinterpret_cast<float*>(vbytes + (vi * VB + loff)), nv);
+                        if (mine) __stcg(reinterpret_cast<R*>(vbytes + (vi * VB + loff)), (R)nv);
                         if (ballot)
                         {
-                            const unsigned hw = __ballot_sync(FULL, nv < 0.f);
+                            const unsigned hw = __ballot_sync(FULL, A::lt0(nv));
                             if (lane == 0) __stcg(hd + vi, hw);
                         }
                     }
-                    if (mine)
-                        SIO::store(cn, (size_t)c,
-                                   SW == 3 ? make_uint4(__float_as_uint(c1), __float_as_uint(c2), nsg | (neq << 16), 0u)
-                                           : make_uint4(__float_as_uint(c1), __float_as_uint(c2), nsg, neq));
+                    if (mine) SIO::store(cn, (size_t)c, ST::encode(c1, c2, nsg, neq));
                 }
             }
             my_iters += mine ? 1 : 0;
@@ -1382,11 +1424,11 @@ launch_ldpc_t(const LdpcLaunch& a, cudaStream_t s)
     return cudaErrorInvalidValue;
 }
 
-template<int DI>
+template<typename R, int DI>
 static cudaError_t
 launch_ldpc_coop_k(const LdpcLaunch& a, cudaStream_t s)
 {
-    auto k = ldpc_decode_coop_kernel<DI>;
+    auto k = ldpc_decode_coop_kernel<R, DI>;
     const size_t smem = ((size_t)a.M * ((DI + 1) / 2) + a.M + 1 + 4 * COOP_WORKERS + COOP_WORKERS * 320 + 2) * sizeof(uint32_t);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1403,13 +1445,28 @@ ldpc_coop_min_reuse()
     return COOP_MIN_REUSE;
 }
 
-// float, one frame per lane, one round: the cooperative small-batch kernel
+// float or int16, one frame per lane, one round: the cooperative small-batch kernel
 cudaError_t
-launch_ldpc_decode_coop(const LdpcLaunch& a, cudaStream_t s)
+launch_ldpc_decode_coop(const LdpcLaunch& a, int precision, cudaStream_t s)
 {
-    if (a.d_info == 25) return launch_ldpc_coop_k<25>(a, s);
-    if (a.d_info == 9) return launch_ldpc_coop_k<9>(a, s);
+    if (precision == 0)
+    {
+        if (a.d_info == 25) return launch_ldpc_coop_k<float, 25>(a, s);
+        if (a.d_info == 9) return launch_ldpc_coop_k<float, 9>(a, s);
+    }
+    else if (precision == 1)
+    {
+        if (a.d_info == 25) return launch_ldpc_coop_k<int16_t, 25>(a, s);
+        if (a.d_info == 9) return launch_ldpc_coop_k<int16_t, 9>(a, s);
+    }
     return cudaErrorInvalidValue;
+}
+
+// bytes of the cooperative kernel's check state per (check, frame)
+int
+ldpc_coop_state_bytes(int precision, int d_info)
+{
+    return precision == 0 ? 4 * ldpc_state_words(d_info) : 12;
 }
 
 cudaError_t

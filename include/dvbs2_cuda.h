@@ -97,7 +97,7 @@ extern "C"
         int ldpc_frames_per_lane;    /* f32 only: frames per lane of round 1, 1 (32-frame groups: lowest latency) or 2
                                       * (64-frame groups, 256-byte chunks: highest throughput); 0 = chosen per call from
                                       * the batch size (1 while the call fits in one wave of 32-frame groups)           */
-        int ldpc_coop_max_frames;    /* f32 only: calls of up to this many frames (with one frame per lane) use the
+        int ldpc_coop_max_frames;    /* f32 and int16: calls of up to this many frames (with one frame per lane) use the
                                       * cooperative small-batch LDPC kernel — a CTA per 32-frame group, ~10x shorter calls
                                       * below a few thousand frames, one round, same results; 0 = default 16384, < 0 = never */
         int host_pipeline_chunks;    /* host-buffer entry points: how many chunks a call is split into over the handle's

@@ -11,7 +11,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "dvbs2_b200", "libdvbs2_cuda.so")
 HOT = ["ldpc_decode_kernelIfLi25ELi2ELb0", "ldpc_decode_kernelIfLi9ELi2ELb0", "ldpc_decode_kernelIfLi25ELi1ELb0",
-       "ldpc_decode_kernelIsLi25ELi4ELb1", "ldpc_decode_kernelIsLi9ELi4ELb1", "ldpc_decode_coop_kernelILi25E",
+       "ldpc_decode_kernelIsLi25ELi4ELb1", "ldpc_decode_kernelIsLi9ELi4ELb1", "ldpc_decode_coop_kernelIfLi25E", "ldpc_decode_coop_kernelIsLi25E",
        "ldpc_onchip_kernelILi25ELi3ELb1", "demap_to_var_kernelILi2EfLi2ELi0", "demap_to_var_kernelILi3EfLi2ELi0",
        "demap_to_var_kernelILi2EfLi2ELi2", "bch_remainder_kernel", "bch_correct_kernel", "unpack_bytes_kernel"]
 WATCH = ["VIADD.16x2", "VIMNMX.S16x2", "VIADDMNMX.S16x2", "VIMNMX3", "FMNMX", "MUFU.EX2", "MUFU.LG2", "SYNCS", "VOTE", "REDUX", "LDG.E.64",

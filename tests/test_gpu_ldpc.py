@@ -32,6 +32,15 @@ def _decode(modcod, Y, prec="f32", n_ite=10, norm=1.0, early_stop=True, compacti
         for k in ("frames", "ldpc_iterations", "ldpc_failures", "iter_hist"):
             assert d[3][k] == c[3][k], k
         return c
+    if prec == "i16" and "ldpc_coop_max_frames" not in cfg:
+        # int16 calls of this size go to the cooperative small-batch kernel (one frame per lane); the packed-halfword lane = frame
+        # kernel (what large batches use) must give the same bits, CWD, iteration counts and statistics
+        a = _decode(modcod, Y, prec, n_ite, norm, early_stop, compaction, ldpc_coop_max_frames=0, **cfg)
+        b = _decode(modcod, Y, prec, n_ite, norm, early_stop, compaction, ldpc_coop_max_frames=-1, **cfg)
+        assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3]))
+        for k in ("frames", "ldpc_iterations", "ldpc_failures", "iter_hist"):
+            assert a[3][k] == b[3][k], k
+        return b
     from dvbs2_b200 import Decoder_LDPC_DVBS2_cuda, Handle
 
     F = Y.shape[0]
