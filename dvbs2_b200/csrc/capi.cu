@@ -101,6 +101,7 @@ struct dvbs2_cuda_handle
     // the next call polls the event (no synchronisation) and picks its schedule from the mean iteration count of the calls
     // completed so far: see pick_schedule().  The memory regions are laid out for the widest hand-over threshold any
     // schedule uses (layout_eighths).
+    bool async_pending = false; // a dvbs2_cuda_chain_compact_async call has been queued and not yet collected by dvbs2_cuda_wait
     bool adaptive = false;
     int layout_eighths = 4;
     unsigned long long* stat_mirror = nullptr; // pinned: {STAT_FRAMES, STAT_LDPC_ITERS, STAT_LDPC_FAIL} as of the last read-back
@@ -1246,6 +1247,11 @@ extern "C"
         if (n_frames == 0) return DVBS2_OK;
         NvtxRange nvtx_range(llr8 ? "dvbs2_cuda_decode_llr8" : pl_frames ? "dvbs2_cuda_rx_chain" : "dvbs2_cuda_chain");
         CU(h, cudaSetDevice(h->cfg.device));
+        if (h->async_pending)
+        { // one call in flight per handle (its staging buffers are about to be reused): collect the previous one first
+            h->async_pending = false;
+            TRY(sync_pipes(h));
+        }
         LaunchScope launch_scope(h);
         const size_t inf = llr8 ? (size_t)N_LDPC
                                 : (size_t)(pl_frames ? pl_frame_symbols(h->mc.n_sym) : h->mc.n_sym) * iq_symbol_bytes(iq_fmt);
@@ -1282,7 +1288,11 @@ extern "C"
                 if (n_iter) CU(h, cudaMemcpyAsync(n_iter + f0, d_nit, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, s));
                 return DVBS2_OK;
             }();
-        if (rc == DVBS2_OK && !wait) return DVBS2_OK; // the *_async entry point: dvbs2_cuda_wait() collects the call
+        if (rc == DVBS2_OK && !wait)
+        { // the *_async entry point: dvbs2_cuda_wait() collects the call
+            h->async_pending = true;
+            return DVBS2_OK;
+        }
         const int rs = sync_pipes(h); // also after a failure: nothing queued may outlive the call
         return rc != DVBS2_OK ? rc : rs;
     }
@@ -1330,6 +1340,7 @@ extern "C"
     {
         if (!h) return DVBS2_ERR_INVALID;
         CU(h, cudaSetDevice(h->cfg.device));
+        h->async_pending = false;
         return sync_pipes(h);
     }
 

@@ -214,7 +214,7 @@ extern "C"
      * the kernels and the D2H copies of the call on the handle's pipeline streams and returns; dvbs2_cuda_wait() blocks until
      * they have finished (and returns the first CUDA error).  The host buffers must be page-locked (dvbs2_cuda_host_register,
      * otherwise the copies are synchronous anyway) and must stay untouched until dvbs2_cuda_wait returns; one call in flight
-     * per handle.  One host thread can thus keep several handles — several GPUs — busy: queue on each, then wait on each.
+     * per handle (a second chain call on the handle first waits for the pending one).  One host thread can thus keep several handles — several GPUs — busy: queue on each, then wait on each.
      * A failure while queueing waits for what was already queued before it returns, like the synchronous entry points. */
     int dvbs2_cuda_chain_compact_async(dvbs2_cuda_handle* h, int iq_format, float iq_scale, const float* CP, const void* Y_N1,
                                        float* SIG, int8_t* CWD_ldpc, int8_t* CWD_bch, int32_t* V_K, uint8_t* V_K_packed,
