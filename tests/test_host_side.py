@@ -220,3 +220,23 @@ def test_committed_bench_line_follows_the_driver_contract():
     ref = json.load(open(os.path.join(ROOT, "profiles", "r2_final_bench_reference_arm.json")))
     assert ref["impl"] == "reference" and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] == "reference"
+
+
+def test_sc12_wire_format_round_trip():
+    """12-bit samples, three bytes per symbol (DVBS2_IQ_SC12): I = bits 0..11, Q = bits 12..23 of a little-endian word —
+    pack / unpack of the Python mirror are inverse up to half an LSB, saturate at +-2047 and keep the sign."""
+    from dvbs2_b200.modules import iq_pack, iq_unpack
+
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((7, 32)) * 1.3).astype(np.float32)
+    x[0, :4] = [5.0, -5.0, 0.0, -1.0 / 512]  # beyond full scale (+-4.0 at LSB 2^-9), zero, one negative LSB
+    w = iq_pack(x, "sc12", 1.0 / 512)
+    assert w.dtype == np.uint8 and w.shape == (7, 48)
+    y = iq_unpack(w, "sc12", 1.0 / 512)
+    assert y.shape == x.shape
+    inside = np.abs(x) < 3.99
+    assert np.abs(y - x)[inside].max() <= 0.5 / 512 + 1e-7
+    assert y[0, 0] == 2047 / 512 and y[0, 1] == -2047 / 512 and y[0, 2] == 0.0 and y[0, 3] == -1.0 / 512
+    # byte layout of one symbol: I = 0x123, Q = -2 (0xffe)
+    one = iq_pack(np.array([[0x123 / 512, -2 / 512]], np.float32), "sc12", 1.0 / 512)
+    assert one.tolist() == [[0x23, 0xe1, 0xff]]
